@@ -1,0 +1,12 @@
+"""red-diffeq_b200 -- B200 (sm_100a) implementation of RED-DiffEq's FD wave-solver hot path.
+
+Public surface (same names as the reference package exports for this path):
+    FWIForward, v_normalize, v_denormalize, s_normalize_none
+Import it as ``red_diffeq_b200`` (the shim red_diffeq_b200.py at the repo root maps the importable
+name onto this directory, whose name has a hyphen).
+"""
+from .solvers.pde import FWIForward
+from .utils.data_trans import s_normalize_none, v_denormalize, v_normalize
+
+__version__ = "0.1.0"
+__all__ = ["FWIForward", "v_normalize", "v_denormalize", "s_normalize_none"]

@@ -1,0 +1,387 @@
+// rdfwi_api.cu -- C ABI (include/rdfwi.h) and the host-side time-loop orchestration.
+//
+// The reference's FWM (solvers/pde.py:61-86) is a Python loop of nt iterations over the whole (B, ns)
+// batch.  Here the batch is advanced in *chunks* of models whose three live levels fit in the L2 cache:
+// a chunk runs its whole time loop before the next one starts, so that p_{t-1} and p_{t-2} of a level
+// are L2 hits and HBM only sees the history write (forward) / history read (adjoint).
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+#include "rdfwi_common.cuh"
+
+namespace rdfwi {
+
+static thread_local std::string t_error;
+static thread_local int64_t t_launches = 0;
+
+void set_error(const std::string &msg) { t_error = msg; }
+void count_launch() { ++t_launches; }
+
+namespace {
+
+#define RD_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+            return RDFWI_ECUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+size_t align_up(size_t n, size_t a) { return (n + a - 1) / a * a; }
+
+int chunk_models(const Plan &p, int B)
+{
+    int nb = p.chunk_models;
+    if (nb <= 0) {
+        int l2 = 0;
+        if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p.device) != cudaSuccess || l2 <= 0) l2 = 64 << 20;
+        // three live levels (p_{t-1}, p_{t-2}, p_t) of every shot of the chunk in ~40% of L2
+        const double per_model = 3.0 * p.g.ns * (double)p.g.level * sizeof(float);
+        nb = (int)std::max(1.0, std::floor(0.4 * l2 / per_model));
+    }
+    nb = std::min(nb, B);
+    const int nchunks = (B + nb - 1) / nb;
+    return (B + nchunks - 1) / nchunks;  // even out the chunks
+}
+
+// Carve-up of the caller's workspace.
+struct Workspace {
+    float *alpha = nullptr, *kap = nullptr, *velmin = nullptr, *beta_src = nullptr, *minpart = nullptr;
+    int *argmin = nullptr;
+    float *fields = nullptr;  // 3 rotating levels of one chunk
+    float *zero = nullptr;    // one zero level of one chunk (p_{-1}, p_{-2})
+    float *Ga = nullptr, *Gk = nullptr, *Gb = nullptr, *fold_tmp = nullptr;
+    double *vel_part = nullptr;
+    size_t bytes = 0;
+    size_t chunk_level = 0;  // floats of one level of a full chunk
+    int nb = 0;
+};
+
+Workspace carve(const Plan &p, int B, void *base)
+{
+    Workspace w;
+    const Grid &g = p.g;
+    w.nb = chunk_models(p, B);
+    w.chunk_level = (size_t)w.nb * g.ns * g.level;
+    size_t off = 0;
+    char *b = static_cast<char *>(base);
+    auto take = [&](size_t nbytes) {
+        char *ptr = b ? b + off : nullptr;
+        off += align_up(nbytes, 256);
+        return ptr;
+    };
+    w.alpha = (float *)take((size_t)B * g.level * 4);
+    w.kap = (float *)take((size_t)B * (g.nbc + 1) * 4);
+    w.velmin = (float *)take((size_t)B * 4);
+    w.argmin = (int *)take((size_t)B * 4);
+    w.beta_src = (float *)take((size_t)B * g.ns * 4);
+    w.minpart = (float *)take((size_t)B * kMinBlocks * 2 * 4);
+    w.fields = (float *)take(3 * w.chunk_level * 4);
+    w.zero = (float *)take(w.chunk_level * 4);
+    w.Ga = (float *)take((size_t)B * g.level * 4);
+    w.Gk = (float *)take((size_t)B * g.level * 4);
+    w.Gb = (float *)take((size_t)B * g.ns * 4);
+    w.fold_tmp = (float *)take((size_t)B * g.nz * g.nxp * 4);
+    w.vel_part = (double *)take((size_t)B * kMinBlocks * 8);
+    w.bytes = off;
+    return w;
+}
+
+int check_common(rdfwi_plan plan, const void *v, int B, const void *ws, size_t ws_bytes)
+{
+    if (!plan) { set_error("null plan"); return RDFWI_EINVAL; }
+    if (!v || B <= 0) { set_error("null velocity pointer or B <= 0"); return RDFWI_EINVAL; }
+    if (!ws) { set_error("null workspace"); return RDFWI_EINVAL; }
+    const Plan &p = *reinterpret_cast<Plan *>(plan);
+    const size_t need = carve(p, B, nullptr).bytes;
+    if (ws_bytes < need) {
+        set_error("workspace too small: need " + std::to_string(need) + " bytes, got " + std::to_string(ws_bytes));
+        return RDFWI_ESIZE;
+    }
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) { set_error("workspace must be 256-byte aligned"); return RDFWI_EINVAL; }
+    return RDFWI_OK;
+}
+
+size_t history_floats(const Plan &p, int B, int segment)
+{
+    if (segment != 0) return 0;
+    return (size_t)B * p.g.ns * (size_t)std::max(p.nt - 1, 0) * p.g.level;
+}
+
+}  // namespace
+}  // namespace rdfwi
+
+using namespace rdfwi;
+
+extern "C" {
+
+int rdfwi_version(void) { return RDFWI_VERSION; }
+const char *rdfwi_last_error(void) { return t_error.c_str(); }
+int64_t rdfwi_last_launch_count(void) { return t_launches; }
+
+int rdfwi_plan_create(const rdfwi_survey *s, rdfwi_plan *out)
+{
+    if (!s || !out) { set_error("null argument"); return RDFWI_EINVAL; }
+    *out = nullptr;
+    if (s->nz < 1 || s->nx < 1 || s->nbc < 2 || s->ns < 1 || s->nrec < 1 || s->nt < 1 || s->sample_temporal < 1) {
+        set_error("invalid survey: need nz,nx,ns,nrec,nt,sample_temporal >= 1 and nbc >= 2");
+        return RDFWI_EINVAL;
+    }
+    if (!s->isx || !s->igx || !s->wavelet) { set_error("null geometry / wavelet pointer"); return RDFWI_EINVAL; }
+    if (!(s->dx > 0) || !(s->dt > 0)) { set_error("dx and dt must be positive"); return RDFWI_EINVAL; }
+    const int nzp = s->nz + 2 * s->nbc, nxp = s->nx + 2 * s->nbc;
+    if (nxp < 8 || nzp < 8) { set_error("padded grid must be at least 8 x 8"); return RDFWI_EINVAL; }
+    if ((double)nzp * ((nxp + 3) / 4 * 4) > 2.0e9) { set_error("padded grid too large for 32-bit cell indices"); return RDFWI_EINVAL; }
+    if (s->isz < 0 || s->isz >= nzp || s->igz < 0 || s->igz >= nzp) { set_error("source / receiver row outside the padded grid"); return RDFWI_EINVAL; }
+    for (int i = 0; i < s->ns; ++i)
+        if (s->isx[i] < 0 || s->isx[i] >= nxp) { set_error("source column outside the padded grid"); return RDFWI_EINVAL; }
+    for (int i = 0; i < s->nrec; ++i)
+        if (s->igx[i] < 0 || s->igx[i] >= nxp) { set_error("receiver column outside the padded grid"); return RDFWI_EINVAL; }
+
+    Plan *p = new Plan();
+    RD_CUDA(cudaGetDevice(&p->device));
+    Grid &g = p->g;
+    g.nz = s->nz; g.nx = s->nx; g.nbc = s->nbc; g.nzp = nzp; g.nxp = nxp;
+    g.pitch = (nxp + 3) / 4 * 4; g.q4 = g.pitch / 4;
+    g.ns = s->ns; g.nrec = s->nrec;
+    g.nt_out = (s->nt + s->sample_temporal - 1) / s->sample_temporal;
+    g.isz = s->isz; g.igz = s->igz;
+    g.level = (unsigned long long)nzp * g.pitch;
+    p->nt = s->nt; p->st = s->sample_temporal;
+    p->dx = s->dx; p->dt = s->dt;
+    p->dx_f = (float)s->dx; p->dt_f = (float)s->dt;
+    // get_Abc: a = (nbc-1)*dx (python float), kappa = 3.0*velmin*np.log(1e7)/(2.0*a)   (solvers/pde.py:42-43)
+    const double a_d = (double)(s->nbc - 1) * s->dx;
+    p->a_f = (float)a_d;
+    p->two_a_f = (float)(2.0 * a_d);
+    p->log1e7_f = (float)std::log(10000000.0);
+    p->wavelet.resize(s->nt);
+    for (int t = 0; t < s->nt; ++t) p->wavelet[t] = (float)s->wavelet[t];
+
+    // host tables
+    std::vector<float> r2(s->nbc + 1), dkap(s->nbc + 1);
+    const float dkappa0 = (3.0f * p->log1e7_f) / p->two_a_f;
+    for (int k = 0; k < s->nbc; ++k) {
+        volatile float r = ((float)k * p->dx_f);  // (dimrange*dx/a)**2, one rounding per op (:46)
+        r = r / p->a_f;
+        volatile float rr = r * r;
+        r2[k] = rr;
+        dkap[k] = (dkappa0 * rr) * p->dt_f;
+    }
+    r2[s->nbc] = 0.0f;
+    dkap[s->nbc] = 0.0f;
+    std::vector<int> rec_ptr(nxp + 1, 0), rec_idx(s->nrec);
+    for (int r = 0; r < s->nrec; ++r) rec_ptr[s->igx[r] + 1]++;
+    for (int x = 0; x < nxp; ++x) rec_ptr[x + 1] += rec_ptr[x];
+    {
+        std::vector<int> fill(rec_ptr.begin(), rec_ptr.end() - 1);
+        for (int r = 0; r < s->nrec; ++r) rec_idx[fill[s->igx[r]]++] = r;
+    }
+    auto upload = [&](auto **dst, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc((void **)dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = upload(&p->d_isx, s->isx, sizeof(int) * s->ns);
+    if (e == cudaSuccess) e = upload(&p->d_rec_ptr, rec_ptr.data(), sizeof(int) * rec_ptr.size());
+    if (e == cudaSuccess) e = upload(&p->d_rec_idx, rec_idx.data(), sizeof(int) * rec_idx.size());
+    if (e == cudaSuccess) e = upload(&p->d_r2, r2.data(), sizeof(float) * r2.size());
+    if (e == cudaSuccess) e = upload(&p->d_dkap, dkap.data(), sizeof(float) * dkap.size());
+    if (e != cudaSuccess) {
+        set_error(std::string("plan tables: ") + cudaGetErrorString(e));
+        rdfwi_plan_destroy(reinterpret_cast<rdfwi_plan>(p));
+        return RDFWI_ECUDA;
+    }
+    *out = reinterpret_cast<rdfwi_plan>(p);
+    return RDFWI_OK;
+}
+
+int rdfwi_plan_destroy(rdfwi_plan plan)
+{
+    if (!plan) return RDFWI_OK;
+    Plan *p = reinterpret_cast<Plan *>(plan);
+    DeviceGuard guard(p->device);
+    cudaFree(p->d_isx); cudaFree(p->d_rec_ptr); cudaFree(p->d_rec_idx); cudaFree(p->d_r2); cudaFree(p->d_dkap);
+    delete p;
+    return RDFWI_OK;
+}
+
+int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
+{
+    if (!plan || !key) { set_error("null argument"); return RDFWI_EINVAL; }
+    Plan *p = reinterpret_cast<Plan *>(plan);
+    const std::string k(key);
+    if (k == "chunk_models") { if (value < 0) goto bad; p->chunk_models = (int)value; }
+    else if (k == "rows_per_thread") { if (value != 1 && value != 2 && value != 4) goto bad; p->rows_per_thread = (int)value; }
+    else if (k == "adj_rows_per_thread") { if (value != 1 && value != 2) goto bad; p->adj_rows_per_thread = (int)value; }
+    else if (k == "use_graph") { p->use_graph = value != 0; }
+    else { set_error("unknown option " + k); return RDFWI_EINVAL; }
+    return RDFWI_OK;
+bad:
+    set_error("invalid value for option " + k);
+    return RDFWI_EINVAL;
+}
+
+int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
+{
+    if (!plan || !key || !out) { set_error("null argument"); return RDFWI_EINVAL; }
+    Plan *p = reinterpret_cast<Plan *>(plan);
+    const std::string k(key);
+    if (k == "chunk_models") *out = p->chunk_models;
+    else if (k == "rows_per_thread") *out = p->rows_per_thread;
+    else if (k == "adj_rows_per_thread") *out = p->adj_rows_per_thread;
+    else if (k == "use_graph") *out = p->use_graph;
+    else if (k == "pitch") *out = p->g.pitch;
+    else if (k == "nzp") *out = p->g.nzp;
+    else if (k == "nxp") *out = p->g.nxp;
+    else if (k == "nt_out") *out = p->g.nt_out;
+    else { set_error("unknown option " + k); return RDFWI_EINVAL; }
+    return RDFWI_OK;
+}
+
+size_t rdfwi_level_floats(rdfwi_plan plan) { return plan ? (size_t) reinterpret_cast<Plan *>(plan)->g.level : 0; }
+
+size_t rdfwi_workspace_bytes(rdfwi_plan plan, int32_t B)
+{
+    if (!plan || B <= 0) return 0;
+    return carve(*reinterpret_cast<Plan *>(plan), B, nullptr).bytes;
+}
+
+size_t rdfwi_history_bytes(rdfwi_plan plan, int32_t B, int32_t segment)
+{
+    if (!plan || B <= 0) return 0;
+    return history_floats(*reinterpret_cast<Plan *>(plan), B, segment) * sizeof(float);
+}
+
+int rdfwi_coefficients(rdfwi_plan plan, const float *v, int32_t B, float *alpha_pad, float *kappa_tab, float *velmin,
+                       int32_t *argmin, float *beta_src, void *ws, size_t ws_bytes, void *stream)
+{
+    int rc = check_common(plan, v, B, ws, ws_bytes);
+    if (rc) return rc;
+    if (!alpha_pad || !kappa_tab || !velmin || !argmin || !beta_src) { set_error("null output"); return RDFWI_EINVAL; }
+    const Plan &p = *reinterpret_cast<Plan *>(plan);
+    DeviceGuard guard(p.device);
+    t_launches = 0;
+    Workspace w = carve(p, B, ws);
+    RD_CUDA(launch_coefficients(p, v, B, alpha_pad, kappa_tab, velmin, argmin, beta_src, w.minpart, (cudaStream_t)stream));
+    return RDFWI_OK;
+}
+
+int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void *ws, size_t ws_bytes, void *history,
+                  size_t history_bytes, int32_t segment, void *stream)
+{
+    int rc = check_common(plan, v, B, ws, ws_bytes);
+    if (rc) return rc;
+    if (!seis) { set_error("null seismogram buffer"); return RDFWI_EINVAL; }
+    const Plan &p = *reinterpret_cast<Plan *>(plan);
+    const Grid &g = p.g;
+    if (history) {
+        if (segment != 0) { set_error("checkpointed history (segment > 0) is not available in this build"); return RDFWI_EINVAL; }
+        if (history_bytes < history_floats(p, B, segment) * sizeof(float)) { set_error("history buffer too small"); return RDFWI_ESIZE; }
+    }
+    DeviceGuard guard(p.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    t_launches = 0;
+    Workspace w = carve(p, B, ws);
+    RD_CUDA(launch_coefficients(p, v, B, w.alpha, w.kap, w.velmin, w.argmin, w.beta_src, w.minpart, st));
+    float *hist = static_cast<float *>(history);
+    const int nt = p.nt;
+    if (hist) RD_CUDA(cudaMemsetAsync(w.zero, 0, w.chunk_level * sizeof(float), st));
+
+    for (int b0 = 0; b0 < B; b0 += w.nb) {
+        const int nb = std::min(w.nb, B - b0);
+        const size_t lvl = (size_t)nb * g.ns * g.level;  // floats per level of this chunk
+        float *hbase = hist ? hist + (size_t)b0 * g.ns * (size_t)(nt - 1) * g.level : nullptr;
+        if (!hist) RD_CUDA(cudaMemsetAsync(w.fields, 0, 3 * w.chunk_level * sizeof(float), st));
+        auto level_ptr = [&](int t) -> float * {
+            if (hist) {
+                if (t < 0) return w.zero;
+                if (t <= nt - 2) return hbase + (size_t)t * lvl;
+                return w.fields;
+            }
+            return w.fields + (size_t)((t + 3) % 3) * w.chunk_level;
+        };
+        for (int t = 0; t < nt; ++t) {
+            FwdArgs a;
+            a.p1 = level_ptr(t - 1);
+            a.p0 = level_ptr(t - 2);
+            a.out = level_ptr(t);
+            a.alpha = w.alpha + (size_t)b0 * g.level;
+            a.kap = w.kap + (size_t)b0 * (g.nbc + 1);
+            a.beta_src = w.beta_src + (size_t)b0 * g.ns;
+            a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
+            a.seis = (t % p.st == 0) ? seis + (size_t)b0 * g.ns * g.nt_out * g.nrec : nullptr;
+            a.it_out = t / p.st;
+            a.w_t = p.wavelet[t];
+            launch_fwd_step(p, a, nb, st);
+        }
+    }
+    RD_CUDA(cudaGetLastError());
+    return RDFWI_OK;
+}
+
+int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot, float *grad_v, void *ws, size_t ws_bytes,
+                   const void *history, size_t history_bytes, int32_t segment, void *stream)
+{
+    int rc = check_common(plan, v, B, ws, ws_bytes);
+    if (rc) return rc;
+    if (!cot || !grad_v || !history) { set_error("null cotangent / gradient / history"); return RDFWI_EINVAL; }
+    const Plan &p = *reinterpret_cast<Plan *>(plan);
+    const Grid &g = p.g;
+    if (segment != 0) { set_error("checkpointed history (segment > 0) is not available in this build"); return RDFWI_EINVAL; }
+    if (history_bytes < history_floats(p, B, segment) * sizeof(float)) { set_error("history buffer too small"); return RDFWI_ESIZE; }
+    DeviceGuard guard(p.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    t_launches = 0;
+    Workspace w = carve(p, B, ws);
+    RD_CUDA(launch_coefficients(p, v, B, w.alpha, w.kap, w.velmin, w.argmin, w.beta_src, w.minpart, st));
+    RD_CUDA(cudaMemsetAsync(w.zero, 0, w.chunk_level * sizeof(float), st));
+    RD_CUDA(cudaMemsetAsync(w.Ga, 0, (size_t)B * g.level * sizeof(float), st));
+    RD_CUDA(cudaMemsetAsync(w.Gk, 0, (size_t)B * g.level * sizeof(float), st));
+    RD_CUDA(cudaMemsetAsync(w.Gb, 0, (size_t)B * g.ns * sizeof(float), st));
+    const float *hist = static_cast<const float *>(history);
+    const int nt = p.nt;
+
+    for (int b0 = 0; b0 < B; b0 += w.nb) {
+        const int nb = std::min(w.nb, B - b0);
+        const size_t lvl = (size_t)nb * g.ns * g.level;
+        const float *hbase = hist + (size_t)b0 * g.ns * (size_t)(nt - 1) * g.level;
+        RD_CUDA(cudaMemsetAsync(w.fields, 0, 3 * w.chunk_level * sizeof(float), st));  // q_{nt} = q_{nt+1} = 0
+        for (int t = nt - 1; t >= 0; --t) {
+            AdjArgs a;
+            a.q1 = w.fields + (size_t)((t + 1) % 3) * w.chunk_level;
+            a.q2 = w.fields + (size_t)((t + 2) % 3) * w.chunk_level;
+            a.out = w.fields + (size_t)(t % 3) * w.chunk_level;
+            a.pm1 = t >= 1 ? hbase + (size_t)(t - 1) * lvl : w.zero;
+            a.alpha = w.alpha + (size_t)b0 * g.level;
+            a.kap = w.kap + (size_t)b0 * (g.nbc + 1);
+            a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
+            a.cot = (t % p.st == 0) ? cot + (size_t)b0 * g.ns * g.nt_out * g.nrec : nullptr;
+            a.it_out = t / p.st;
+            a.w_t = p.wavelet[t];
+            a.Ga = w.Ga + (size_t)b0 * g.level;
+            a.Gk = w.Gk + (size_t)b0 * g.level;
+            a.Gb = w.Gb + (size_t)b0 * g.ns;
+            launch_adj_step(p, a, nb, st);
+        }
+    }
+    RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.velmin, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
+    return RDFWI_OK;
+}
+
+}  // extern "C"

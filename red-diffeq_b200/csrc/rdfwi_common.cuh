@@ -1,0 +1,107 @@
+// rdfwi_common.cuh -- shared declarations of the sm_100a wave-solver library (see include/rdfwi.h).
+//
+// Wavefield layout in HBM ("pitched periodic layout")
+//   One time level of one shot is nzp rows of `pitch` floats, pitch = nxp rounded up to 4, so every
+//   row starts 16-byte aligned and a thread owns one float4 = 4 consecutive cells of a row.
+//   Columns nxp .. pitch-1 are *periodic images* of columns 0 .. pitch-nxp-1: they are computed with
+//   the coefficients of the cells they mirror, so they always hold bit-identical copies and the
+//   float4 holding the last real columns sees its right-hand neighbours in-register.  This is how the
+//   reference's torch.roll wrap-around (solvers/pde.py:79) is honoured without a branch in the
+//   stencil; only the four scalar x-neighbour loads and the row offsets use wrapped indices.
+//   Levels of the shots of one "chunk" of models are contiguous: level(t)[shot][z][x].
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include <string>
+#include <vector>
+
+#include "rdfwi.h"
+
+namespace rdfwi {
+
+constexpr int kThreads = 256;      // threads per CTA of the step kernels
+constexpr int kMinBlocks = 32;     // CTAs per model in the min/arg-min and velmin-term reductions
+
+// Geometry every kernel needs, passed by value (lives in constant bank).
+struct Grid {
+    int nz, nx, nbc;    // unpadded model, sponge width
+    int nzp, nxp;       // padded grid
+    int pitch, q4;      // floats per row, float4 per row
+    int ns, nrec, nt_out;
+    int isz, igz;
+    unsigned long long level;  // nzp * pitch floats
+};
+
+struct Plan {
+    int device = 0;
+    Grid g{};
+    int nt = 0, st = 1;
+    double dx = 0, dt = 0;
+    float dx_f = 0, dt_f = 0;
+    float a_f = 0, two_a_f = 0, log1e7_f = 0;  // get_Abc constants (solvers/pde.py:42-43)
+    std::vector<float> wavelet;                // fp32 cast of the host wavelet (what `tensor * src[i]` uses)
+    // device tables (owned)
+    int *d_isx = nullptr;      // (ns)
+    int *d_rec_ptr = nullptr;  // (nxp+1) CSR: receivers sitting in each padded column
+    int *d_rec_idx = nullptr;  // (nrec)
+    float *d_r2 = nullptr;     // (nbc+1) (k*dx/a)^2, entry nbc = 0
+    float *d_dkap = nullptr;   // (nbc+1) d(kappa*dt)/d(velmin) per profile entry, entry nbc = 0
+    // options
+    int chunk_models = 0;   // 0 = auto
+    int rows_per_thread = 2;
+    int use_graph = 0;
+    int adj_rows_per_thread = 1;
+};
+
+// Pointers of one step launch (forward).
+struct FwdArgs {
+    const float *p1;        // level t-1 of the chunk
+    const float *p0;        // level t-2
+    float *out;             // level t
+    const float *alpha;     // (nb, nzp, pitch)
+    const float *kap;       // (nb, nbc+1)
+    const float *beta_src;  // (nb, ns)
+    const int *isx;
+    const int *rec_ptr;
+    const int *rec_idx;
+    float *seis;            // (nb, ns, nt_out, nrec) or nullptr when this level is not sampled
+    int it_out;
+    float w_t;
+};
+
+struct AdjArgs {
+    const float *q1;   // q_{t+1}
+    const float *q2;   // q_{t+2}
+    float *out;        // q_t
+    const float *pm1;  // forward level t-1 (zeros for t = 0)
+    const float *alpha;
+    const float *kap;
+    const int *isx;
+    const int *rec_ptr;
+    const int *rec_idx;
+    const float *cot;  // (nb, ns, nt_out, nrec) or nullptr when level t carries no cotangent
+    int it_out;
+    float w_t;
+    float *Ga;  // (nb, nzp, pitch)  sum_t,s q_t (S-5) p_{t-1}
+    float *Gk;  // (nb, nzp, pitch)  sum_t,s (q_{t+1}-q_t) p_{t-1}
+    float *Gb;  // (nb, ns)          sum_t   q_t[src] w_t
+};
+
+void set_error(const std::string &msg);
+void count_launch();
+
+// kernels_prologue.cu
+cudaError_t launch_coefficients(const Plan &p, const float *v, int B, float *alpha_pad, float *kap, float *velmin,
+                                int *argmin, float *beta_src, float *minpart, cudaStream_t st);
+// kernels_step.cu
+cudaError_t launch_fwd_step(const Plan &p, const FwdArgs &a, int nb, cudaStream_t st);
+cudaError_t launch_adj_step(const Plan &p, const AdjArgs &a, int nb, cudaStream_t st);
+// kernels_epilogue.cu
+cudaError_t launch_gradient_epilogue(const Plan &p, const float *v, int B, const float *Ga, const float *Gk,
+                                     const float *Gb, const float *velmin, const int *argmin, float *fold_tmp,
+                                     double *vel_part, float *grad_v, cudaStream_t st);
+
+}  // namespace rdfwi
