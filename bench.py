@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- FD forward+adjoint throughput of the B200 path (and of the CPU reference arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one gradient evaluation of the hot path over one batch of synthetic velocity models:
+forward modelling of every shot (nt levels) + the reverse-time adjoint with the imaging condition,
+i.e. B*ns*nzp*nxp*nt forward+adjoint cell-update *pairs* (SURVEY.md 8d).  Default workload = BASELINE.json
+configs[1] (OpenFWI 70x70, 64 models x 5 shots x 1000 levels) on one GPU; with N GPUs every rank runs its
+own 64 models (models are independent: weak scaling, no data-path collective).
+
+Prints ONE JSON line (see the keys at the bottom).  `value` is measured with inputs resident in HBM,
+`e2e` through the public operator (FWIForward + autograd) from pinned host buffers.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_FWD = 12.0   # read p_{t-1}, p_{t-2}; write p_t                      
+ALGO_BYTES_ADJ = 16.0   # read q_{t+1}, q_{t+2}, p_{t-1}; write q_t
+ALGO_BYTES_PAIR = ALGO_BYTES_FWD + ALGO_BYTES_ADJ
+
+WORKLOADS = {
+    # name: (pde ctx factory, nz, nx, models per GPU)
+    "openfwi_b64": ("openfwi", 70, 70, 64),
+    "openfwi_b1": ("openfwi", 70, 70, 1),
+    "marmousi_b1": ("marmousi", 70, 190, 1),
+    "marmousi_b16": ("marmousi", 70, 190, 16),
+}
+
+
+def make_ctx(kind):
+    from red_diffeq_b200.utils import synthetic
+    return dict(synthetic.PDE_OPENFWI if kind == "openfwi" else synthetic.PDE_MARMOUSI)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax = float(r[1])
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # only samples under load (top half) describe the timed region
+        sm_load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(sm_load)) if sm_load else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(ctx, nz, nx, target_seconds=20.0):
+    """Times the oracle port (CPU restatement of the reference algorithm) on a bounded sample of the workload."""
+    from oracle import build_oracle, fwi_oracle
+    from red_diffeq_b200.utils import synthetic
+    build_oracle.build()
+    threads = fwi_oracle.threads()
+    sv = fwi_oracle.Survey(dict(ctx), nz, nx)
+    B = max(1, -(-threads // sv.ns))          # one shot per host thread
+    B = min(B, 32)
+    vn = synthetic.velocity_models(B, nz, nx, seed=99)
+    v_phys = (vn + np.float32(1)) / np.float32(2) * np.float32(3000) + np.float32(1500)
+    cot = synthetic.cotangent((B, sv.ns, sv.nt_out, sv.nrec), seed=100)
+    best, reps, t_total = None, 0, 0.0
+    while reps < 3 and (reps == 0 or t_total < target_seconds):
+        t0 = time.perf_counter()
+        fwi_oracle.gradient(sv, v_phys, cot)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        reps += 1
+        t_total += dt
+    pairs = sv.pairs(B)
+    return {"value": pairs / best, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"oracle C port (OpenMP, {threads} threads), {B} models x {sv.ns} shots x {sv.nt} levels, "
+                      f"fwd+adjoint, best of {reps} ({best:.2f} s)"}, pairs, best
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference algorithm on the host CPU (oracle port; the Python reference cannot travel)."""
+    if rank != 0:
+        return
+    kind, nz, nx, B = WORKLOADS[args.workload]
+    ctx = make_ctx(kind)
+    times, pairs, base = [], None, None
+    for i in range(args.warmup + args.steps):
+        base, pairs, best = cpu_baseline(ctx, nz, nx, target_seconds=0.0)
+        if i >= args.warmup:
+            times.append(best)
+    t = float(np.mean(times))
+    value = pairs / t
+    base["value"] = value
+    line = {"impl": "reference", "metric": "FD cell-updates/s (fwd+adjoint)", "value": value, "unit": "pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "note": "bounded CPU sample of the same workload: " + base["sample"]},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="openfwi_b64", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override models per GPU (debugging)")
+    ap.add_argument("--nt", type=int, default=0, help="override time levels (debugging; invalidates the headline)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (e.g. chunk_models=8)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize
+    from red_diffeq_b200.utils import synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    kind, nz, nx, B = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    ctx = make_ctx(kind)
+    if args.nt:
+        ctx["nt"] = args.nt
+    op = FWIForward(dict(ctx), dev, normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        op.set_option(k, int(v))
+    ns, nt, nbc = ctx["ns"], ctx["nt"], ctx["nbc"]
+    nzp, nxp = nz + 2 * nbc, nx + 2 * nbc
+    pairs_rank = B * ns * nzp * nxp * nt
+    cells_level = B * ns * nzp * nxp
+
+    # synthetic inputs (seed 8888 + rank): models, and "observed" data = a fixed random record so that the
+    # L1 misfit of the e2e path has a non-trivial cotangent
+    vn_host = torch.from_numpy(synthetic.velocity_models(B, nz, nx, seed=synthetic.SEED + rank)).pin_memory()
+    y_host = torch.from_numpy(synthetic.cotangent((B, ns, nt, ctx["ng"]), seed=17 + rank)).pin_memory()
+    grad_host = torch.empty((B, 1, nz, nx), dtype=torch.float32).pin_memory()
+    loss_host = torch.empty((B,), dtype=torch.float32).pin_memory()
+    v_dev = vn_host.to(dev)
+    cot_dev = y_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        v = v_dev.detach().requires_grad_(True)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        seis = op(v)
+        launches_f = op.last_launches
+        e1.record()
+        seis.backward(cot_dev)
+        e2.record()
+        return e0, e1, e2, launches_f, op.last_launches - launches_f
+
+    def step_e2e():
+        v = vn_host.to(dev, non_blocking=True).requires_grad_(True)
+        y = y_host.to(dev, non_blocking=True)
+        seis = op(v)
+        loss = (seis - y).abs().mean(dim=(1, 2, 3))          # the reference's L1 data misfit (core/losses.py:27-41)
+        loss.sum().backward()
+        grad_host.copy_(v.grad, non_blocking=True)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+
+    # ---- resident-input timing (value) -------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_stop = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    evs = [step_resident() for _ in range(args.steps)]
+    t_stop.record()
+    barrier()
+    elapsed_ms = t_start.elapsed_time(t_stop)
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    adj_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    launches_f, launches_b = evs[-1][3], evs[-1][4]
+
+    # ---- end-to-end timing from pinned host buffers (e2e) -------------------------------------------
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    barrier()
+    e_start = torch.cuda.Event(enable_timing=True)
+    e_stop = torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e_stop.record()
+    barrier()
+    e2e_ms = e_start.elapsed_time(e_stop)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        ms_per_step = elapsed_ms / args.steps
+        value = pairs_rank * world / (ms_per_step * 1e-3)
+        e2e_value = pairs_rank * world / (e2e_ms / args.steps * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        # dominant kernel = the adjoint step (k_adj_step): all shots of a chunk, one time level per launch
+        step_launches_b = max(launches_b - 7, 1)      # minus prologue (3) + epilogue (4) launches
+        adj_launch_s = adj_ms * 1e-3 / step_launches_b
+        bytes_per_launch = ALGO_BYTES_ADJ * cells_level * nt / step_launches_b
+        achieved = bytes_per_launch / adj_launch_s / 1e9
+        step_launches_f = max(launches_f - 3, 1)
+        fwd_achieved = ALGO_BYTES_FWD * cells_level * nt / (fwd_ms * 1e-3) / 1e9
+        line = {
+            "metric": "FD cell-updates/s (fwd+adjoint)", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "models_per_gpu": B, "shots_per_model": ns, "nt": nt,
+                       "padded_grid": [nzp, nxp], "pairs_per_step_per_gpu": pairs_rank,
+                       "l2_policy": "working set (wavefield history %.1f GB) far exceeds the 126 MB L2; no flush needed"
+                                    % (op._plan_for(nz, nx, dev).history_bytes(B) / 1e9),
+                       "options": dict(op.options)},
+            "e2e": {"value": e2e_value, "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(vn_host.numel() * 4 + y_host.numel() * 4),
+                    "d2h_bytes_per_step": int(grad_host.numel() * 4 + loss_host.numel() * 4)},
+            "gpu_launches": int((launches_f + launches_b) * args.steps),
+            "roofline": {"bound": "hbm", "kernel": "k_adj_step", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": adj_launch_s * 1e6,
+                         "launches_per_step": step_launches_b,
+                         "forward": {"kernel": "k_fwd_step", "achieved": fwd_achieved, "frac": fwd_achieved / peak,
+                                     "avg_launch_us": fwd_ms * 1e3 / step_launches_f, "launches_per_step": step_launches_f},
+                         "pair_frac": (ALGO_BYTES_PAIR * pairs_rank / ((fwd_ms + adj_ms) * 1e-3) / 1e9) / peak},
+            "phase_ms": {"forward": fwd_ms, "adjoint": adj_ms},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            base, _, _ = cpu_baseline(ctx, nz, nx)
+            line["cpu_baseline"] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,316 @@
+// kernels_cluster.cu -- cluster-resident time loop: a whole shot lives in the shared memory of one
+// thread-block cluster for all nt levels.
+//
+// Replaces the same reference code as kernels_step.cu (the hot loop solvers/pde.py:78-85 and, for the
+// adjoint, the autograd replay behind core/inversion.py:86) with identical arithmetic, but removes the
+// per-level HBM round trip of the wavefields: a padded OpenFWI shot is 2 x 387 KB (p_{t-1}, p_{t-2}),
+// which fits the shared memory of a 4-CTA cluster.  Per level each CTA
+//   1. updates its slab of rows in place (p_t overwrites p_{t-2}: a cell needs p_{t-2} only at itself),
+//      z-marching in registers, x-neighbours by warp shuffle;
+//   2. pushes its two first / last rows into the neighbours' halo rows through distributed shared memory
+//      (st.shared::cluster), periodic in z like torch.roll;
+//   3. one barrier.cluster (release/acquire) closes the level;
+//   4. an elected thread streams the slab to the wavefield history with a 1-D bulk copy
+//      (cp.async.bulk shared -> global), overlapped with the next level.
+// HBM traffic: forward = the history write only (4 B / cell-update instead of 12).
+#include "rdfwi_common.cuh"
+
+namespace rdfwi {
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ float lane(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+
+__device__ __forceinline__ int sponge_index(int i, int n, int nbc)
+{
+    return i < nbc ? nbc - 1 - i : (i >= n - nbc ? i - (n - nbc) : -1);
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// store a float4 into the same shared-memory offset of another CTA of the cluster
+__device__ __forceinline__ void st_cluster_v4(const float *local_ptr, uint32_t cta, float4 v)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(cta));
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ void bulk_store(float *gptr, const float *sptr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(smem_u32(sptr)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ forward
+// Hot loop notes (from the ncu captures under profiles/): the kernel is issue-bound, so the row sweep is
+// kept free of branches and address arithmetic:
+//   * PITCH is a template parameter for the production grids (0 = runtime pitch), so every row offset is
+//     an immediate of the LDS/STS instruction;
+//   * the time loop is unrolled by two, which makes "which buffer holds p_{t-1}" a compile-time role;
+//   * rows a thread does not own are still computed (from in-bounds garbage) and only their store is
+//     predicated;
+//   * source injection, receiver sampling and the halo pushes run in a short epilogue, executed by the
+//     threads that own those rows.
+struct FwdThread {
+    int x, la, lb;            // first column, local row range [la, lb)
+    int lac;                  // la clamped into the slab for lanes that own nothing
+    bool edgeL, edgeR;
+    int eL, eR;               // column offsets of the (x-2, x-1) / (x+4, x+5) pairs, periodic
+    bool colsp[4];
+    int src_lr, rec_lr;
+};
+
+template <int RMAX, int PITCH>
+__device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cur, const int prv, const int kap_off,
+                                          const int pitch_rt, const FwdThread &th, const float4 (&al)[RMAX],
+                                          const float (&kapx)[4])
+{
+    const int pitch = PITCH > 0 ? PITCH : pitch_rt;
+    const float c2 = 4.0f / 3.0f, c3 = -1.0f / 12.0f;
+    const float *cb = smem + cur + (2 + th.lac) * pitch + th.x;  // row la of p_{t-1}, this thread's float4
+    float *pb = smem + prv + (2 + th.lac) * pitch + th.x;        // row la of p_{t-2}; p_t goes there
+    const float *eLp = smem + cur + (2 + th.lac) * pitch + th.eL;
+    const float *eRp = smem + cur + (2 + th.lac) * pitch + th.eR;
+    const float *kz = smem + kap_off + th.lac;
+
+    float4 w0 = ld4(cb - 2 * pitch), w1 = ld4(cb - pitch), w2 = ld4(cb), w3 = ld4(cb + pitch);
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+        const float4 w4 = ld4(cb + (r + 2) * pitch);
+        const float4 old = ld4(pb + r * pitch);
+        const float kapz = kz[r];
+        // x-neighbours outside the float4 come from the adjacent lanes' centre vectors
+        float l2 = __shfl_up_sync(0xffffffffu, w2.z, 1);
+        float l1 = __shfl_up_sync(0xffffffffu, w2.w, 1);
+        float r0 = __shfl_down_sync(0xffffffffu, w2.x, 1);
+        float r1 = __shfl_down_sync(0xffffffffu, w2.y, 1);
+        if (th.edgeL) { l2 = eLp[r * pitch]; l1 = eLp[r * pitch + 1]; }
+        if (th.edgeR) { r0 = eRp[r * pitch]; r1 = eRp[r * pitch + 1]; }
+        const float e[8] = {l2, l1, w2.x, w2.y, w2.z, w2.w, r0, r1};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float kp = th.colsp[j] ? kapx[j] : kapz;  // columns override rows (solvers/pde.py:50-51)
+            const float alj = lane(al[r], j);
+            const float s1 = __fadd_rn(__fadd_rn(__fadd_rn(lane(w1, j), lane(w3, j)), e[j + 1]), e[j + 3]);
+            const float s2 = __fadd_rn(__fadd_rn(__fadd_rn(lane(w0, j), lane(w4, j)), e[j]), e[j + 4]);
+            const float lap = __fadd_rn(__fmul_rn(c2, s1), __fmul_rn(c3, s2));
+            const float t1 = __fsub_rn(__fadd_rn(2.0f, __fmul_rn(-5.0f, alj)), kp);  // temp1 (:69)
+            const float t2 = __fsub_rn(1.0f, kp);                                     // temp2 (:70)
+            o[j] = __fadd_rn(__fsub_rn(__fmul_rn(t1, e[j + 2]), __fmul_rn(t2, lane(old, j))), __fmul_rn(alj, lap));
+        }
+        if (th.la + r < th.lb) st4(pb + r * pitch, make_float4(o[0], o[1], o[2], o[3]));
+        w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+    }
+}
+
+template <int RMAX, int PITCH>
+__global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdArgs a, Grid g)
+{
+    extern __shared__ __align__(128) float smem[];
+
+    const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+    const int cid = blockIdx.x / C, ncl = gridDim.x / C;
+    const int base = g.nzp / C, rem = g.nzp % C;
+    const int nrows = base + (rank < rem ? 1 : 0);
+    const int r0 = rank * base + (rank < rem ? rank : rem);
+    const int up = rank == 0 ? C - 1 : rank - 1;
+    const int dn = rank == C - 1 ? 0 : rank + 1;
+    const int nrows_up = base + (up < rem ? 1 : 0);
+
+    const int pitch = PITCH > 0 ? PITCH : g.pitch;
+    const int slab = (a.slabrows + 4) * pitch;  // floats per buffer: 2 halo rows, slab rows, 2 halo rows
+    const int kap_off = 2 * slab;               // per-row sponge value of the CTA's rows (slabrows floats)
+
+    const int tid = threadIdx.x, lane_id = tid & 31;
+    const int grp = tid / g.q4, col = tid - grp * g.q4;
+    const bool active = grp < a.ngroups;
+    const bool warp_active = (tid - lane_id) < a.ngroups * g.q4;  // warps without any owner lane skip the sweep
+    FwdThread th;
+    th.x = col * 4;
+    th.la = grp * RMAX;
+    th.lb = !active ? th.la : (th.la + RMAX < nrows ? th.la + RMAX : nrows);
+    th.lac = active ? th.la : 0;
+    th.edgeL = lane_id == 0 || col == 0;
+    th.edgeR = lane_id == 31 || col == g.q4 - 1;
+    th.eL = col == 0 ? g.nxp - 2 : th.x - 2;
+    th.eR = col == g.q4 - 1 ? pitch - g.nxp : th.x + 4;
+    int xc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        xc[j] = th.x + j >= g.nxp ? th.x + j - g.nxp : th.x + j;
+        th.colsp[j] = sponge_index(xc[j], g.nxp, g.nbc) >= 0;
+    }
+    // rows this thread must handle in the epilogue (local row index, or -1)
+    th.src_lr = (g.isz - r0 >= th.la && g.isz - r0 < th.lb) ? g.isz - r0 : -1;
+    th.rec_lr = (g.igz - r0 >= th.la && g.igz - r0 < th.lb) ? g.igz - r0 : -1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t hist_shot = (size_t)(a.nt - 1) * g.level;
+
+    for (int shot = cid; shot < a.nshots; shot += ncl) {
+        const int b = shot / g.ns, s = shot - b * g.ns;
+        // p_{-1} = p_{-2} = 0 (halo rows included); sponge tables of this model
+        for (int i = tid; i < 2 * slab; i += kClusterThreads) smem[i] = 0.0f;
+        const float *kap_b = a.kap + (size_t)b * (g.nbc + 1);
+        for (int i = tid; i < a.slabrows; i += kClusterThreads) {
+            const int kz = sponge_index(r0 + i, g.nzp, g.nbc);
+            smem[kap_off + i] = (i < nrows && kz >= 0) ? kap_b[kz] : 0.0f;
+        }
+        float4 al[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+            al[r] = (th.la + r < th.lb) ? ld4(a.alpha + (size_t)b * g.level + (size_t)(r0 + th.la + r) * pitch + th.x) : zero4;
+        float kapx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kx = sponge_index(xc[j], g.nxp, g.nbc);
+            kapx[j] = kx >= 0 ? kap_b[kx] : 0.0f;
+        }
+        const int xs = a.isx[s];
+        int src_mask = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) src_mask |= (th.src_lr >= 0 && xc[j] == xs) ? (1 << j) : 0;
+        const float bsrc = a.beta_src[shot];
+        __syncthreads();
+        cluster_sync_all();  // every CTA of the cluster has cleared its buffers before halos are pushed
+
+        // one time level: p_{t-1} in buffer `cur`, p_{t-2} in `prv`, p_t overwrites p_{t-2}
+        auto level = [&](const int t, const int cur, const int prv) {
+            const int p0 = prv + 2 * pitch + th.x;
+            if (warp_active) {
+                fwd_sweep<RMAX, PITCH>(smem, cur, prv, kap_off, pitch, th, al, kapx);
+                if (src_mask != 0) {  // p[src] += beta_dt[src] * wavelet[t]   (solvers/pde.py:80-81)
+                    const float src_add = __fmul_rn(bsrc, a.wavelet[t]);
+                    float4 v = ld4(smem + p0 + th.src_lr * pitch);
+                    if (src_mask & 1) v.x = __fadd_rn(v.x, src_add);
+                    if (src_mask & 2) v.y = __fadd_rn(v.y, src_add);
+                    if (src_mask & 4) v.z = __fadd_rn(v.z, src_add);
+                    if (src_mask & 8) v.w = __fadd_rn(v.w, src_add);
+                    st4(smem + p0 + th.src_lr * pitch, v);
+                }
+                if (th.rec_lr >= 0 && t % a.st == 0) {  // sampled after injection (solvers/pde.py:82-83)
+                    float *seis_t = a.seis + ((size_t)shot * g.nt_out + t / a.st) * g.nrec;
+                    const float4 v = ld4(smem + p0 + th.rec_lr * pitch);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (th.x + j < g.nxp)
+                            for (int k = a.rec_ptr[th.x + j]; k < a.rec_ptr[th.x + j + 1]; ++k) seis_t[a.rec_idx[k]] = lane(v, j);
+                }
+                // halo rows of the neighbours (periodic ring over the cluster, like torch.roll in z)
+                if (th.la < 2)
+                    for (int h = th.la; h < 2 && h < th.lb; ++h)
+                        st_cluster_v4(smem + prv + (2 + nrows_up + h) * pitch + th.x, (uint32_t)up, ld4(smem + p0 + h * pitch));
+                if (th.lb > nrows - 2)
+                    for (int h = (th.la > nrows - 2 ? th.la : nrows - 2); h < th.lb; ++h)
+                        st_cluster_v4(smem + prv + (h - (nrows - 2)) * pitch + th.x, (uint32_t)dn, ld4(smem + p0 + h * pitch));
+            }
+            if (a.hist != nullptr) {
+                fence_proxy_async();             // slab writes -> visible to the bulk-copy engine
+                if (tid == 0) bulk_wait_read();  // the copy of the previous level has finished reading its buffer
+            }
+            cluster_sync_all();
+            if (a.hist != nullptr && tid == 0 && t <= a.nt - 2)
+                bulk_store(a.hist + (size_t)shot * hist_shot + (size_t)t * g.level + (size_t)r0 * pitch,
+                           smem + prv + 2 * pitch, (uint32_t)(nrows * pitch * sizeof(float)));
+        };
+        int t = 0;
+        for (; t + 1 < a.nt; t += 2) {
+            level(t, 0, slab);
+            level(t + 1, slab, 0);
+        }
+        if (t < a.nt) level(t, 0, slab);
+        if (a.hist != nullptr && tid == 0) bulk_wait_read();
+        __syncthreads();
+    }
+    if (tid == 0) bulk_wait_all();
+}
+
+}  // namespace
+
+bool cluster_config(const Plan &p, ClusterConfig *cfg)
+{
+    const Grid &g = p.g;
+    const int groups_max = kClusterThreads / g.q4;
+    if (groups_max < 1) return false;
+    int max_smem = 0;
+    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device) != cudaSuccess) return false;
+    for (int C = 1; C <= 8; ++C) {
+        if (p.cluster_size > 0 && C != p.cluster_size) continue;
+        if (g.nzp / C < 2) break;
+        const int maxrows = (g.nzp + C - 1) / C;
+        const int ngroups = (maxrows + kClusterRowsMax - 1) / kClusterRowsMax;  // each thread marches kClusterRowsMax rows
+        if (ngroups > groups_max) continue;
+        const int slabrows = ngroups * kClusterRowsMax;  // >= maxrows: rows past the slab are computed but never stored
+        const size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 8) * sizeof(float);
+        if (smem > (size_t)max_smem) continue;
+        cfg->C = C; cfg->maxrows = maxrows; cfg->ngroups = ngroups; cfg->slabrows = slabrows; cfg->smem = smem;
+        return true;
+    }
+    return false;
+}
+
+template <int PITCH>
+static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
+{
+    auto kernel = k_fwd_cluster<kClusterRowsMax, PITCH>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
+    if (e != cudaSuccess) return e;
+    a.slabrows = cc.slabrows; a.ngroups = cc.ngroups;
+
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cc.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.dynamicSmemBytes = cc.smem;
+    cfg.stream = st;
+    // persistent: as many clusters as can be co-resident (or one per shot if fewer shots)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+    cfg.gridDim = dim3((unsigned)(sms / cc.C * cc.C));
+    int max_clusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg);
+    if (e != cudaSuccess) return e;
+    if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
+    const int ncl = max_clusters < a.nshots ? max_clusters : a.nshots;
+    cfg.gridDim = dim3((unsigned)(ncl * cc.C));
+    e = cudaLaunchKernelEx(&cfg, kernel, a, p.g);
+    count_launch();
+    return e;
+}
+
+cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
+{
+    switch (p.g.pitch) {  // production grids get immediate row offsets (OpenFWI 310+2, Marmousi/Overthrust 430+2)
+        case 312: return launch_fwd_cluster_t<312>(p, cc, a, st);
+        case 432: return launch_fwd_cluster_t<432>(p, cc, a, st);
+        default: return launch_fwd_cluster_t<0>(p, cc, a, st);
+    }
+}
+
+}  // namespace rdfwi

@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(kThreads) k_fwd_step(FwdArgs a, Grid g)
     const float c3 = -1.0f / 12.0f;
 
     for (int s = 0; s < g.ns; ++s) {
-        const size_t so = (size_t)(b * g.ns + s) * g.level;
-        const float *__restrict__ P1 = a.p1 + so;
-        const float *__restrict__ P0 = a.p0 + so;
-        float *__restrict__ PO = a.out + so;
+        const size_t shot = (size_t)(b * g.ns + s);
+        const float *__restrict__ P1 = a.p1 + shot * a.ss_p1;
+        const float *__restrict__ P0 = a.p0 + shot * a.ss_p0;
+        float *__restrict__ PO = a.out + shot * a.ss_out;
 
         float4 rows[R + 4];
 #pragma unroll
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) k_adj_step(AdjArgs a, Grid g)
         const size_t so = (size_t)(b * g.ns + s) * g.level;
         const float *__restrict__ Q1 = a.q1 + so;
         const float *__restrict__ Q2 = a.q2 + so;
-        const float *__restrict__ PM = a.pm1 + so;
+        const float *__restrict__ PM = a.pm1 + (size_t)(b * g.ns + s) * a.ss_pm1;
         float *__restrict__ QO = a.out + so;
 
         float4 qrow[R + 4], prow[R + 4];

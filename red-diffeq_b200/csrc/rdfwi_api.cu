@@ -202,6 +202,7 @@ int rdfwi_plan_create(const rdfwi_survey *s, rdfwi_plan *out)
     if (e == cudaSuccess) e = upload(&p->d_rec_idx, rec_idx.data(), sizeof(int) * rec_idx.size());
     if (e == cudaSuccess) e = upload(&p->d_r2, r2.data(), sizeof(float) * r2.size());
     if (e == cudaSuccess) e = upload(&p->d_dkap, dkap.data(), sizeof(float) * dkap.size());
+    if (e == cudaSuccess) e = upload(&p->d_wavelet, p->wavelet.data(), sizeof(float) * p->wavelet.size());
     if (e != cudaSuccess) {
         set_error(std::string("plan tables: ") + cudaGetErrorString(e));
         rdfwi_plan_destroy(reinterpret_cast<rdfwi_plan>(p));
@@ -216,7 +217,7 @@ int rdfwi_plan_destroy(rdfwi_plan plan)
     if (!plan) return RDFWI_OK;
     Plan *p = reinterpret_cast<Plan *>(plan);
     DeviceGuard guard(p->device);
-    cudaFree(p->d_isx); cudaFree(p->d_rec_ptr); cudaFree(p->d_rec_idx); cudaFree(p->d_r2); cudaFree(p->d_dkap);
+    cudaFree(p->d_isx); cudaFree(p->d_rec_ptr); cudaFree(p->d_rec_idx); cudaFree(p->d_r2); cudaFree(p->d_dkap); cudaFree(p->d_wavelet);
     delete p;
     return RDFWI_OK;
 }
@@ -230,6 +231,8 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "rows_per_thread") { if (value != 1 && value != 2 && value != 4) goto bad; p->rows_per_thread = (int)value; }
     else if (k == "adj_rows_per_thread") { if (value != 1 && value != 2) goto bad; p->adj_rows_per_thread = (int)value; }
     else if (k == "use_graph") { p->use_graph = value != 0; }
+    else if (k == "engine") { if (value < 0 || value > 2) goto bad; p->engine = (int)value; }
+    else if (k == "cluster_size") { if (value < 0 || value > 8) goto bad; p->cluster_size = (int)value; }
     else { set_error("unknown option " + k); return RDFWI_EINVAL; }
     return RDFWI_OK;
 bad:
@@ -246,6 +249,9 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
     else if (k == "rows_per_thread") *out = p->rows_per_thread;
     else if (k == "adj_rows_per_thread") *out = p->adj_rows_per_thread;
     else if (k == "use_graph") *out = p->use_graph;
+    else if (k == "engine") *out = p->engine;
+    else if (k == "cluster_size") *out = p->cluster_size;
+    else if (k == "cluster_size_used") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cc.C : 0; }
     else if (k == "pitch") *out = p->g.pitch;
     else if (k == "nzp") *out = p->g.nzp;
     else if (k == "nxp") *out = p->g.nxp;
@@ -301,26 +307,41 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
     RD_CUDA(launch_coefficients(p, v, B, w.alpha, w.kap, w.velmin, w.argmin, w.beta_src, w.minpart, st));
     float *hist = static_cast<float *>(history);
     const int nt = p.nt;
+    ClusterConfig cc;
+    if (p.engine != 1 && cluster_config(p, &cc)) {
+        // cluster-resident time loop: one launch for all shots and all levels
+        ClusterFwdArgs a{};
+        a.alpha = w.alpha; a.kap = w.kap; a.beta_src = w.beta_src;
+        a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx; a.wavelet = p.d_wavelet;
+        a.seis = seis; a.hist = hist;
+        a.nshots = B * g.ns; a.nt = nt; a.st = p.st;
+        RD_CUDA(launch_fwd_cluster(p, cc, a, st));
+        return RDFWI_OK;
+    }
+    if (p.engine == 2) { set_error("engine=2 (cluster-resident) requested but the grid does not fit a cluster"); return RDFWI_EINVAL; }
     if (hist) RD_CUDA(cudaMemsetAsync(w.zero, 0, w.chunk_level * sizeof(float), st));
 
     for (int b0 = 0; b0 < B; b0 += w.nb) {
         const int nb = std::min(w.nb, B - b0);
         const size_t lvl = (size_t)nb * g.ns * g.level;  // floats per level of this chunk
-        float *hbase = hist ? hist + (size_t)b0 * g.ns * (size_t)(nt - 1) * g.level : nullptr;
+        const size_t hstride = (size_t)(nt - 1) * g.level;  // shot stride inside the history
+        float *hbase = hist ? hist + (size_t)b0 * g.ns * hstride : nullptr;
         if (!hist) RD_CUDA(cudaMemsetAsync(w.fields, 0, 3 * w.chunk_level * sizeof(float), st));
-        auto level_ptr = [&](int t) -> float * {
+        (void)lvl;
+        auto level_ptr = [&](int t, unsigned long long *stride) -> float * {
+            *stride = g.level;
             if (hist) {
                 if (t < 0) return w.zero;
-                if (t <= nt - 2) return hbase + (size_t)t * lvl;
+                if (t <= nt - 2) { *stride = hstride; return hbase + (size_t)t * g.level; }
                 return w.fields;
             }
             return w.fields + (size_t)((t + 3) % 3) * w.chunk_level;
         };
         for (int t = 0; t < nt; ++t) {
             FwdArgs a;
-            a.p1 = level_ptr(t - 1);
-            a.p0 = level_ptr(t - 2);
-            a.out = level_ptr(t);
+            a.p1 = level_ptr(t - 1, &a.ss_p1);
+            a.p0 = level_ptr(t - 2, &a.ss_p0);
+            a.out = level_ptr(t, &a.ss_out);
             a.alpha = w.alpha + (size_t)b0 * g.level;
             a.kap = w.kap + (size_t)b0 * (g.nbc + 1);
             a.beta_src = w.beta_src + (size_t)b0 * g.ns;
@@ -360,14 +381,17 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     for (int b0 = 0; b0 < B; b0 += w.nb) {
         const int nb = std::min(w.nb, B - b0);
         const size_t lvl = (size_t)nb * g.ns * g.level;
-        const float *hbase = hist + (size_t)b0 * g.ns * (size_t)(nt - 1) * g.level;
+        const size_t hstride = (size_t)(nt - 1) * g.level;
+        const float *hbase = hist + (size_t)b0 * g.ns * hstride;
+        (void)lvl;
         RD_CUDA(cudaMemsetAsync(w.fields, 0, 3 * w.chunk_level * sizeof(float), st));  // q_{nt} = q_{nt+1} = 0
         for (int t = nt - 1; t >= 0; --t) {
             AdjArgs a;
             a.q1 = w.fields + (size_t)((t + 1) % 3) * w.chunk_level;
             a.q2 = w.fields + (size_t)((t + 2) % 3) * w.chunk_level;
             a.out = w.fields + (size_t)(t % 3) * w.chunk_level;
-            a.pm1 = t >= 1 ? hbase + (size_t)(t - 1) * lvl : w.zero;
+            a.pm1 = t >= 1 ? hbase + (size_t)(t - 1) * g.level : w.zero;
+            a.ss_pm1 = t >= 1 ? hstride : g.level;
             a.alpha = w.alpha + (size_t)b0 * g.level;
             a.kap = w.kap + (size_t)b0 * (g.nbc + 1);
             a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;

@@ -8,7 +8,9 @@
 //   float4 holding the last real columns sees its right-hand neighbours in-register.  This is how the
 //   reference's torch.roll wrap-around (solvers/pde.py:79) is honoured without a branch in the
 //   stencil; only the four scalar x-neighbour loads and the row offsets use wrapped indices.
-//   Levels of the shots of one "chunk" of models are contiguous: level(t)[shot][z][x].
+//   Rotating scratch levels are stored level(t)[shot][z][x]; the wavefield history is shot-major,
+//   hist[shot][t][z][x] for t = 0 .. nt-2, so one shot's levels stream contiguously (the cluster-resident
+//   kernels write / read them with 1-D bulk copies) and the per-level kernels address it with a shot stride.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -24,6 +26,8 @@ namespace rdfwi {
 
 constexpr int kThreads = 256;      // threads per CTA of the step kernels
 constexpr int kMinBlocks = 32;     // CTAs per model in the min/arg-min and velmin-term reductions
+constexpr int kClusterThreads = 512;  // threads per CTA of the cluster-resident kernels (<= 128 registers each)
+constexpr int kClusterRowsMax = 13;   // rows marched per thread there (coefficients stay in registers)
 
 // Geometry every kernel needs, passed by value (lives in constant bank).
 struct Grid {
@@ -49,11 +53,37 @@ struct Plan {
     int *d_rec_idx = nullptr;  // (nrec)
     float *d_r2 = nullptr;     // (nbc+1) (k*dx/a)^2, entry nbc = 0
     float *d_dkap = nullptr;   // (nbc+1) d(kappa*dt)/d(velmin) per profile entry, entry nbc = 0
+    float *d_wavelet = nullptr;  // (nt) fp32 wavelet for the cluster-resident kernels
     // options
     int chunk_models = 0;   // 0 = auto
     int rows_per_thread = 2;
     int use_graph = 0;
     int adj_rows_per_thread = 1;
+    int engine = 0;         // 0 = auto, 1 = per-level kernels, 2 = cluster-resident time loop
+    int cluster_size = 0;   // 0 = smallest cluster that fits
+};
+
+// Cluster-resident forward time loop (kernels_cluster.cu).
+struct ClusterFwdArgs {
+    const float *alpha;     // (B, nzp, pitch)
+    const float *kap;       // (B, nbc+1)
+    const float *beta_src;  // (B*ns)
+    const int *isx;
+    const int *rec_ptr;
+    const int *rec_idx;
+    const float *wavelet;   // (nt) device
+    float *seis;            // (B*ns, nt_out, nrec)
+    float *hist;            // [shot][t][z][x], t = 0..nt-2, or nullptr
+    int nshots, nt, st;
+    int slabrows, ngroups;  // filled by launch_fwd_cluster from the ClusterConfig
+};
+
+struct ClusterConfig {
+    int C = 0;        // CTAs per cluster = row slabs per shot
+    int maxrows = 0;  // rows of the largest slab
+    int ngroups = 0;  // row groups per CTA (threads = ngroups * q4), kClusterRowsMax rows per thread
+    int slabrows = 0; // ngroups * kClusterRowsMax >= maxrows (rows allocated per buffer, halos excluded)
+    size_t smem = 0;  // dynamic shared memory per CTA
 };
 
 // Pointers of one step launch (forward).
@@ -70,6 +100,7 @@ struct FwdArgs {
     float *seis;            // (nb, ns, nt_out, nrec) or nullptr when this level is not sampled
     int it_out;
     float w_t;
+    unsigned long long ss_p1, ss_p0, ss_out;  // floats between consecutive shots in p1 / p0 / out
 };
 
 struct AdjArgs {
@@ -88,6 +119,7 @@ struct AdjArgs {
     float *Ga;  // (nb, nzp, pitch)  sum_t,s q_t (S-5) p_{t-1}
     float *Gk;  // (nb, nzp, pitch)  sum_t,s (q_{t+1}-q_t) p_{t-1}
     float *Gb;  // (nb, ns)          sum_t   q_t[src] w_t
+    unsigned long long ss_pm1;  // floats between consecutive shots in pm1 (history or the zero level)
 };
 
 void set_error(const std::string &msg);
@@ -99,6 +131,9 @@ cudaError_t launch_coefficients(const Plan &p, const float *v, int B, float *alp
 // kernels_step.cu
 cudaError_t launch_fwd_step(const Plan &p, const FwdArgs &a, int nb, cudaStream_t st);
 cudaError_t launch_adj_step(const Plan &p, const AdjArgs &a, int nb, cudaStream_t st);
+// kernels_cluster.cu
+bool cluster_config(const Plan &p, ClusterConfig *cfg);
+cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st);
 // kernels_epilogue.cu
 cudaError_t launch_gradient_epilogue(const Plan &p, const float *v, int B, const float *Ga, const float *Gk,
                                      const float *Gb, const float *velmin, const int *argmin, float *fold_tmp,

@@ -21,6 +21,29 @@ from .. import _cabi
 from . import survey as _survey
 
 
+class _HistoryLease:
+    """Exclusive use of one wavefield-history buffer between a forward call and its backward.
+
+    The buffers are owned by the operator and reused from one inversion iteration to the next: the
+    history is by far the largest allocation (115 GiB for 64 OpenFWI models) and must not be carved up by
+    the caching allocator between iterations.
+    """
+
+    def __init__(self, arena, buffer):
+        self.arena, self.buffer = arena, buffer
+
+    def release(self):
+        if self.buffer is not None:
+            self.arena.append(self.buffer)
+            self.buffer = None
+
+    def __del__(self):  # graph dropped without backward
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class _WaveSolve(torch.autograd.Function):
     """seismograms = F(v_phys); backward = discrete adjoint."""
 
@@ -38,27 +61,29 @@ class _WaveSolve(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[0]
         with torch.cuda.device(v.device):
             stream = torch.cuda.current_stream().cuda_stream
+            hist, hist_bytes, lease = None, 0, None
+            if need_grad:
+                hist_bytes = plan.history_bytes(B, 0)
+                lease = op._lease_history(hist_bytes, v.device)
+                hist = lease.buffer
             seis = torch.empty((B, plan.ns, plan.nt_out, plan.nrec), dtype=torch.float32, device=v.device)
             ws_bytes = plan.workspace_bytes(B)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
-            hist, hist_bytes = None, 0
-            if need_grad:
-                hist_bytes = plan.history_bytes(B, 0)
-                hist = op._alloc_history(hist_bytes, v.device)
             plan.forward(v.data_ptr(), B, seis.data_ptr(), ws.data_ptr(), ws_bytes,
                          hist.data_ptr() if hist is not None else None, hist_bytes, 0, stream)
             op.last_launches = plan.last_launch_count()
         if need_grad:
-            ctx.op, ctx.plan, ctx.hist, ctx.hist_bytes = op, plan, hist, hist_bytes
+            ctx.op, ctx.plan, ctx.hist, ctx.hist_bytes = op, plan, lease, hist_bytes
             ctx.save_for_backward(v)
         return seis
 
     @staticmethod
     def backward(ctx, grad_seis):
         (v,) = ctx.saved_tensors
-        plan, hist = ctx.plan, ctx.hist
-        if hist is None:
+        plan, lease = ctx.plan, ctx.hist
+        if lease is None:
             raise RuntimeError("rdfwi: backward called twice or without saved history")
+        hist = lease.buffer
         B = v.shape[0]
         g = grad_seis.contiguous()
         if g.dtype != torch.float32:
@@ -71,7 +96,8 @@ class _WaveSolve(torch.autograd.Function):
             plan.backward(v.data_ptr(), B, g.data_ptr(), grad_v.data_ptr(), ws.data_ptr(), ws_bytes,
                           hist.data_ptr(), ctx.hist_bytes, 0, stream)
             ctx.op.last_launches += plan.last_launch_count()
-        ctx.hist = None  # release the wavefield history (first-order only, like every caller in the reference)
+        ctx.hist = None  # first-order only, like every caller in the reference
+        lease.release()  # hand the wavefield history back to the operator's arena
         return grad_v, None
 
 
@@ -98,6 +124,7 @@ class FWIForward(nn.Module):
         self.sample_temporal = sample_temporal
         self.ctx = _survey.complete_ctx(ctx, sample_spatial)
         self._plans = {}
+        self._history_arena = {}
         self._lock = threading.Lock()
         self.last_launches = 0
         self.options = {}
@@ -134,14 +161,28 @@ class FWIForward(nn.Module):
                 self._plans[key] = plan
         return plan
 
-    def _alloc_history(self, nbytes, device):
+    def _lease_history(self, nbytes, device):
+        """A history buffer of at least nbytes on `device`, reused across iterations when idle."""
+        key = str(device)
+        with self._lock:
+            arena = self._history_arena.setdefault(key, [])
+            for i, buf in enumerate(arena):
+                if buf.numel() >= nbytes:
+                    return _HistoryLease(arena, arena.pop(i))
+            arena.clear()  # idle buffers that are too small: give them back before growing
         free, _total = torch.cuda.mem_get_info(device)
         reserved_free = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
         if nbytes > free + reserved_free:
             raise torch.cuda.OutOfMemoryError(
                 f"rdfwi: the wavefield history needs {nbytes / 2**30:.1f} GiB but only "
                 f"{(free + reserved_free) / 2**30:.1f} GiB is available; reduce the batch")
-        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return _HistoryLease(arena, torch.empty(nbytes, dtype=torch.uint8, device=device))
+
+    def release_memory(self):
+        """Drop the idle wavefield-history buffers held for reuse."""
+        with self._lock:
+            for arena in self._history_arena.values():
+                arena.clear()
 
     # -- the operator -----------------------------------------------------------------------------
     def forward(self, v):
