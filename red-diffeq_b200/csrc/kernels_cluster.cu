@@ -13,57 +13,10 @@
 //   4. an elected thread streams the slab to the wavefield history with a 1-D bulk copy
 //      (cp.async.bulk shared -> global), overlapped with the next level.
 // HBM traffic: forward = the history write only (4 B / cell-update instead of 12).
-#include "rdfwi_common.cuh"
+#include "cluster_ptx.cuh"
 
 namespace rdfwi {
 namespace {
-
-__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
-__device__ __forceinline__ float lane(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
-
-__device__ __forceinline__ int sponge_index(int i, int n, int nbc)
-{
-    return i < nbc ? nbc - 1 - i : (i >= n - nbc ? i - (n - nbc) : -1);
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// store a float4 into the same shared-memory offset of another CTA of the cluster
-__device__ __forceinline__ void st_cluster_v4(const float *local_ptr, uint32_t cta, float4 v)
-{
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(cta));
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
-
-__device__ __forceinline__ void bulk_store(float *gptr, const float *sptr, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(smem_u32(sptr)), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ forward
 // Hot loop notes (from the ncu captures under profiles/): the kernel is issue-bound, so the row sweep is
@@ -75,18 +28,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //     predicated;
 //   * source injection, receiver sampling and the halo pushes run in a short epilogue, executed by the
 //     threads that own those rows.
-struct FwdThread {
-    int x, la, lb;            // first column, local row range [la, lb)
-    int lac;                  // la clamped into the slab for lanes that own nothing
-    bool edgeL, edgeR;
-    int eL, eR;               // column offsets of the (x-2, x-1) / (x+4, x+5) pairs, periodic
-    bool colsp[4];
-    int src_lr, rec_lr;
-};
 
 template <int RMAX, int PITCH>
 __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cur, const int prv, const int kap_off,
-                                          const int pitch_rt, const FwdThread &th, const float4 (&al)[RMAX],
+                                          const int pitch_rt, const SweepThread &th, const float4 (&al)[RMAX],
                                           const float (&kapx)[4])
 {
     const int pitch = PITCH > 0 ? PITCH : pitch_rt;
@@ -150,7 +95,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     const int grp = tid / g.q4, col = tid - grp * g.q4;
     const bool active = grp < a.ngroups;
     const bool warp_active = (tid - lane_id) < a.ngroups * g.q4;  // warps without any owner lane skip the sweep
-    FwdThread th;
+    SweepThread th;
     th.x = col * 4;
     th.la = grp * RMAX;
     th.lb = !active ? th.la : (th.la + RMAX < nrows ? th.la + RMAX : nrows);

@@ -1,0 +1,353 @@
+// kernels_cluster_adj.cu -- cluster-resident reverse-time loop: adjoint field + zero-lag imaging sums.
+//
+// Replaces what PyTorch autograd replays from the tape of solvers/pde.py:78-85 (core/inversion.py:86).
+// Formulation ("adjoint in the u-variable"): with u_t = alpha * q_t the adjoint recurrence
+//     q_t = T1 q_{t+1} + S(alpha q_{t+1}) - T2 q_{t+2} + R^T g_t                       
+// becomes
+//     u_t = T1 u_{t+1} + alpha S(u_{t+1}) - T2 u_{t+2} + alpha R^T g_t
+// which is the *forward* recurrence with another source term, so the same shared-memory sweep applies
+// (stencil on the stored field itself, no alpha needed at neighbour cells).  The imaging sums become
+//     Ga = (1/alpha) sum_t u_t (S-5) p_{t-1},   Gk = (1/alpha) sum_t (u_{t+1}-u_t) p_{t-1},
+//     Gb = (1/alpha_src) sum_t u_t[src] w_t
+// and stay in registers for the whole time loop (a thread owns the same cells at every level).
+//
+// Shared memory per CTA: two u slabs (with 2+2 halo rows, exchanged through DSMEM as in the forward
+// kernel), one p slab (forward level t-1 with halos, streamed from the HBM history by 1-D bulk copies
+// completing on an mbarrier, issued one level ahead), one alpha slab.
+#include "cluster_ptx.cuh"
+
+namespace rdfwi {
+namespace {
+
+// u_t over the thread's rows: same structure as fwd_sweep, FMA contraction allowed (no bit-parity
+// requirement on the adjoint), alpha read from its shared-memory slab.
+template <int RMAX, int PITCH>
+__device__ __forceinline__ void adj_sweep(float *__restrict__ smem, const int cur, const int prv, const int al_off,
+                                          const int kap_off, const int pitch_rt, const SweepThread &th,
+                                          const float (&kapx)[4])
+{
+    const int pitch = PITCH > 0 ? PITCH : pitch_rt;
+    const float c2 = 4.0f / 3.0f, c3 = -1.0f / 12.0f;
+    const float *cb = smem + cur + (2 + th.lac) * pitch + th.x;
+    float *pb = smem + prv + (2 + th.lac) * pitch + th.x;
+    const float *ab = smem + al_off + th.lac * pitch + th.x;
+    const float *eLp = smem + cur + (2 + th.lac) * pitch + th.eL;
+    const float *eRp = smem + cur + (2 + th.lac) * pitch + th.eR;
+    const float *kz = smem + kap_off + th.lac;
+
+    float4 w0 = ld4(cb - 2 * pitch), w1 = ld4(cb - pitch), w2 = ld4(cb), w3 = ld4(cb + pitch);
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+        const float4 w4 = ld4(cb + (r + 2) * pitch);
+        const float4 old = ld4(pb + r * pitch);
+        const float4 alv = ld4(ab + r * pitch);
+        const float kapz = kz[r];
+        float l2 = __shfl_up_sync(0xffffffffu, w2.z, 1);
+        float l1 = __shfl_up_sync(0xffffffffu, w2.w, 1);
+        float r0 = __shfl_down_sync(0xffffffffu, w2.x, 1);
+        float r1 = __shfl_down_sync(0xffffffffu, w2.y, 1);
+        if (th.edgeL) { l2 = eLp[r * pitch]; l1 = eLp[r * pitch + 1]; }
+        if (th.edgeR) { r0 = eRp[r * pitch]; r1 = eRp[r * pitch + 1]; }
+        const float e[8] = {l2, l1, w2.x, w2.y, w2.z, w2.w, r0, r1};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float kp = th.colsp[j] ? kapx[j] : kapz;
+            const float alj = lane(alv, j);
+            const float s1 = ((lane(w1, j) + lane(w3, j)) + e[j + 1]) + e[j + 3];
+            const float s2 = ((lane(w0, j) + lane(w4, j)) + e[j]) + e[j + 4];
+            const float lap = c2 * s1 + c3 * s2;
+            const float t1 = (2.0f - 5.0f * alj) - kp;
+            const float t2 = 1.0f - kp;
+            o[j] = (t1 * e[j + 2] - t2 * lane(old, j)) + alj * lap;
+        }
+        if (th.la + r < th.lb) st4(pb + r * pitch, make_float4(o[0], o[1], o[2], o[3]));
+        w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+    }
+}
+
+// imaging sums of one level: Ga += u_t (S-5) p_{t-1},  Gk += (u_{t+1} - u_t) p_{t-1}
+template <int RMAX, int PITCH>
+__device__ __forceinline__ void imaging_sweep(const float *__restrict__ smem, const int ucur, const int uprv, const int pbuf,
+                                              const int pitch_rt, const SweepThread &th, float4 (&Ga)[RMAX],
+                                              float4 (&Gk)[RMAX])
+{
+    const int pitch = PITCH > 0 ? PITCH : pitch_rt;
+    const float c2 = 4.0f / 3.0f, c3 = -1.0f / 12.0f;
+    const float *pb = smem + pbuf + (2 + th.lac) * pitch + th.x;       // p_{t-1}, row la
+    const float *u1b = smem + ucur + (2 + th.lac) * pitch + th.x;      // u_{t+1}
+    const float *utb = smem + uprv + (2 + th.lac) * pitch + th.x;      // u_t (just written by this thread)
+    const float *eLp = smem + pbuf + (2 + th.lac) * pitch + th.eL;
+    const float *eRp = smem + pbuf + (2 + th.lac) * pitch + th.eR;
+
+    float4 v0 = ld4(pb - 2 * pitch), v1 = ld4(pb - pitch), v2 = ld4(pb), v3 = ld4(pb + pitch);
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+        const float4 v4 = ld4(pb + (r + 2) * pitch);
+        const float4 ut = ld4(utb + r * pitch);
+        const float4 u1 = ld4(u1b + r * pitch);
+        float l2 = __shfl_up_sync(0xffffffffu, v2.z, 1);
+        float l1 = __shfl_up_sync(0xffffffffu, v2.w, 1);
+        float r0 = __shfl_down_sync(0xffffffffu, v2.x, 1);
+        float r1 = __shfl_down_sync(0xffffffffu, v2.y, 1);
+        if (th.edgeL) { l2 = eLp[r * pitch]; l1 = eLp[r * pitch + 1]; }
+        if (th.edgeR) { r0 = eRp[r * pitch]; r1 = eRp[r * pitch + 1]; }
+        const float e[8] = {l2, l1, v2.x, v2.y, v2.z, v2.w, r0, r1};
+        float ga[4] = {Ga[r].x, Ga[r].y, Ga[r].z, Ga[r].w};
+        float gk[4] = {Gk[r].x, Gk[r].y, Gk[r].z, Gk[r].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float pc = e[j + 2];
+            const float s1 = ((lane(v1, j) + lane(v3, j)) + e[j + 1]) + e[j + 3];
+            const float s2 = ((lane(v0, j) + lane(v4, j)) + e[j]) + e[j + 4];
+            const float lp = (c2 * s1 + c3 * s2) - 5.0f * pc;
+            ga[j] += lane(ut, j) * lp;
+            gk[j] += (lane(u1, j) - lane(ut, j)) * pc;
+        }
+        Ga[r] = make_float4(ga[0], ga[1], ga[2], ga[3]);
+        Gk[r] = make_float4(gk[0], gk[1], gk[2], gk[3]);
+        v0 = v1; v1 = v2; v2 = v3; v3 = v4;
+    }
+}
+
+template <int RMAX, int PITCH>
+__global__ void __launch_bounds__(kClusterThreads, 1) k_adj_cluster(ClusterAdjArgs a, Grid g)
+{
+    extern __shared__ __align__(128) float smem[];
+
+    const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+    const int cid = blockIdx.x / C, ncl = gridDim.x / C;
+    const int base = g.nzp / C, rem = g.nzp % C;
+    const int nrows = base + (rank < rem ? 1 : 0);
+    const int r0 = rank * base + (rank < rem ? rank : rem);
+    const int up = rank == 0 ? C - 1 : rank - 1;
+    const int dn = rank == C - 1 ? 0 : rank + 1;
+    const int nrows_up = base + (up < rem ? 1 : 0);
+
+    const int pitch = PITCH > 0 ? PITCH : g.pitch;
+    const int slab = (a.slabrows + 4) * pitch;
+    const int pbuf = 2 * slab;                    // forward level t-1 with halo rows
+    const int al_off = 3 * slab;                  // alpha of the CTA's rows
+    const int kap_off = al_off + a.slabrows * pitch;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + ((kap_off + a.slabrows + 3) & ~3));
+
+    const int tid = threadIdx.x, lane_id = tid & 31;
+    const int grp = tid / g.q4, col = tid - grp * g.q4;
+    const bool active = grp < a.ngroups;
+    const bool warp_active = (tid - lane_id) < a.ngroups * g.q4;
+    SweepThread th;
+    th.x = col * 4;
+    th.la = grp * RMAX;
+    th.lb = !active ? th.la : (th.la + RMAX < nrows ? th.la + RMAX : nrows);
+    th.lac = active ? th.la : 0;
+    th.edgeL = lane_id == 0 || col == 0;
+    th.edgeR = lane_id == 31 || col == g.q4 - 1;
+    th.eL = col == 0 ? g.nxp - 2 : th.x - 2;
+    th.eR = col == g.q4 - 1 ? pitch - g.nxp : th.x + 4;
+    int xc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        xc[j] = th.x + j >= g.nxp ? th.x + j - g.nxp : th.x + j;
+        th.colsp[j] = sponge_index(xc[j], g.nxp, g.nbc) >= 0;
+    }
+    th.src_lr = (g.isz - r0 >= th.la && g.isz - r0 < th.lb) ? g.isz - r0 : -1;
+    th.rec_lr = (g.igz - r0 >= th.la && g.igz - r0 < th.lb) ? g.igz - r0 : -1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t hist_shot = (size_t)(a.nt - 1) * g.level;
+
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+
+    // stream forward level `lvl` (rows r0-2 .. r0+nrows+1, periodic in z) of `shot` into the p slab
+    auto load_level = [&](const int shot, const int lvl) {
+        const float *src = a.hist + (size_t)shot * hist_shot + (size_t)lvl * g.level;
+        const uint32_t row_b = (uint32_t)(pitch * sizeof(float));
+        const int top = r0 - 2 < 0 ? r0 - 2 + g.nzp : r0 - 2;                      // first halo row (wraps for rank 0)
+        const int bot = r0 + nrows >= g.nzp ? r0 + nrows - g.nzp : r0 + nrows;     // first row below the slab
+        mbar_expect_tx(mbar, (uint32_t)(nrows + 4) * row_b);
+        bulk_load(smem + pbuf, src + (size_t)top * pitch, 2 * row_b, mbar);
+        bulk_load(smem + pbuf + 2 * pitch, src + (size_t)r0 * pitch, (uint32_t)nrows * row_b, mbar);
+        bulk_load(smem + pbuf + (2 + nrows) * pitch, src + (size_t)bot * pitch, 2 * row_b, mbar);
+    };
+
+    for (int shot = cid; shot < a.nshots; shot += ncl) {
+        const int b = shot / g.ns, s = shot - b * g.ns;
+        // u_{nt} = u_{nt+1} = 0; alpha slab and sponge tables of this model
+        for (int i = tid; i < 2 * slab; i += kClusterThreads) smem[i] = 0.0f;
+        const float *kap_b = a.kap + (size_t)b * (g.nbc + 1);
+        const float *alpha_b = a.alpha + (size_t)b * g.level + (size_t)r0 * pitch;
+        for (int i = tid * 4; i < a.slabrows * pitch; i += kClusterThreads * 4)
+            st4(smem + al_off + i, i < nrows * pitch ? ld4(alpha_b + i) : make_float4(1.f, 1.f, 1.f, 1.f));
+        for (int i = tid; i < a.slabrows; i += kClusterThreads) {
+            const int kz = sponge_index(r0 + i, g.nzp, g.nbc);
+            smem[kap_off + i] = (i < nrows && kz >= 0) ? kap_b[kz] : 0.0f;
+        }
+        float kapx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kx = sponge_index(xc[j], g.nxp, g.nbc);
+            kapx[j] = kx >= 0 ? kap_b[kx] : 0.0f;
+        }
+        const int xs = a.isx[s];
+        int src_lane = -1;  // lane of the (non-image) source cell if this thread owns it
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (th.src_lr >= 0 && th.x + j < g.nxp && th.x + j == xs) src_lane = j;
+        float4 Ga[RMAX], Gk[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) { Ga[r] = zero4; Gk[r] = zero4; }
+        float gb = 0.0f;
+        fence_proxy_async();
+        __syncthreads();
+        cluster_sync_all();
+        if (tid == 0 && a.nt >= 2) load_level(shot, a.nt - 2);
+
+        // one reverse level: u_{t+1} in buffer `cur`, u_{t+2} in `prv`, u_t overwrites u_{t+2}
+        auto level = [&](const int t, const int cur, const int prv) {
+            const int p0 = prv + 2 * pitch + th.x;
+            if (warp_active) {
+                adj_sweep<RMAX, PITCH>(smem, cur, prv, al_off, kap_off, pitch, th, kapx);
+                if (th.rec_lr >= 0 && t % a.st == 0) {  // u_t[rec] += alpha * g_t  (adjoint of the gather, :83)
+                    const float *gt = a.cot + ((size_t)shot * g.nt_out + t / a.st) * g.nrec;
+                    float4 v = ld4(smem + p0 + th.rec_lr * pitch);
+                    const float4 alv = ld4(smem + al_off + th.rec_lr * pitch + th.x);
+                    float add[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        for (int k = a.rec_ptr[xc[j]]; k < a.rec_ptr[xc[j] + 1]; ++k) add[j] += gt[a.rec_idx[k]];
+                    v.x += alv.x * add[0]; v.y += alv.y * add[1]; v.z += alv.z * add[2]; v.w += alv.w * add[3];
+                    st4(smem + p0 + th.rec_lr * pitch, v);
+                }
+                if (src_lane >= 0) {  // adjoint of the source injection (:81)
+                    const float4 v = ld4(smem + p0 + th.src_lr * pitch);
+                    gb += (src_lane == 0 ? v.x : src_lane == 1 ? v.y : src_lane == 2 ? v.z : v.w) * a.wavelet[t];
+                }
+                if (th.la < 2)
+                    for (int h = th.la; h < 2 && h < th.lb; ++h)
+                        st_cluster_v4(smem + prv + (2 + nrows_up + h) * pitch + th.x, (uint32_t)up, ld4(smem + p0 + h * pitch));
+                if (th.lb > nrows - 2)
+                    for (int h = (th.la > nrows - 2 ? th.la : nrows - 2); h < th.lb; ++h)
+                        st_cluster_v4(smem + prv + (h - (nrows - 2)) * pitch + th.x, (uint32_t)dn, ld4(smem + p0 + h * pitch));
+            }
+            if (t >= 1) {
+                mbar_wait(mbar, phase);  // forward level t-1 has landed in the p slab
+                phase ^= 1u;
+                if (warp_active) imaging_sweep<RMAX, PITCH>(smem, cur, prv, pbuf, pitch, th, Ga, Gk);
+            }
+            cluster_sync_all();
+            if (tid == 0 && t >= 2) load_level(shot, t - 2);
+        };
+        int t = a.nt - 1;
+        for (; t >= 1; t -= 2) {
+            level(t, 0, slab);
+            level(t - 1, slab, 0);
+        }
+        if (t == 0) level(0, 0, slab);
+
+        // per-shot imaging planes (divided by alpha, see header) -- summed over shots by the epilogue kernels
+        if (active) {
+            float *ga_out = a.Ga + (size_t)shot * g.level + (size_t)(r0 + th.la) * pitch + th.x;
+            float *gk_out = a.Gk + (size_t)shot * g.level + (size_t)(r0 + th.la) * pitch + th.x;
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                if (th.la + r < th.lb) {
+                    const float4 alv = ld4(smem + al_off + (th.la + r) * pitch + th.x);
+                    st4(ga_out + r * pitch, make_float4(Ga[r].x / alv.x, Ga[r].y / alv.y, Ga[r].z / alv.z, Ga[r].w / alv.w));
+                    st4(gk_out + r * pitch, make_float4(Gk[r].x / alv.x, Gk[r].y / alv.y, Gk[r].z / alv.z, Gk[r].w / alv.w));
+                }
+            }
+            if (src_lane >= 0) {
+                const float4 alv = ld4(smem + al_off + th.src_lr * pitch + th.x);
+                a.Gb[shot] = gb / (src_lane == 0 ? alv.x : src_lane == 1 ? alv.y : src_lane == 2 ? alv.z : alv.w);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int RMAX>
+bool adj_config_rmax(const Plan &p, int max_smem, ClusterConfig *cfg)
+{
+    const Grid &g = p.g;
+    const int groups_max = kClusterThreads / g.q4;
+    if (groups_max < 1) return false;
+    for (int C = 1; C <= 8; ++C) {
+        if (p.adj_cluster_size > 0 && C != p.adj_cluster_size) continue;
+        if (g.nzp / C < 2) break;
+        const int maxrows = (g.nzp + C - 1) / C;
+        const int ngroups = (maxrows + RMAX - 1) / RMAX;
+        if (ngroups > groups_max) continue;
+        const int slabrows = ngroups * RMAX;
+        const size_t smem = ((size_t)3 * (slabrows + 4) * g.pitch + (size_t)slabrows * g.pitch + slabrows + 16) * sizeof(float);
+        if (smem > (size_t)max_smem) continue;
+        cfg->C = C; cfg->maxrows = maxrows; cfg->ngroups = ngroups; cfg->slabrows = slabrows; cfg->smem = smem; cfg->rmax = RMAX;
+        return true;
+    }
+    return false;
+}
+
+template <int RMAX, int PITCH>
+cudaError_t launch_adj_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterAdjArgs a, cudaStream_t st)
+{
+    auto kernel = k_adj_cluster<RMAX, PITCH>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
+    if (e != cudaSuccess) return e;
+    a.slabrows = cc.slabrows; a.ngroups = cc.ngroups;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cc.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.dynamicSmemBytes = cc.smem;
+    cfg.stream = st;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+    cfg.gridDim = dim3((unsigned)(sms / cc.C * cc.C));
+    int max_clusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg);
+    if (e != cudaSuccess) return e;
+    if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
+    const int ncl = max_clusters < a.nshots ? max_clusters : a.nshots;
+    cfg.gridDim = dim3((unsigned)(ncl * cc.C));
+    e = cudaLaunchKernelEx(&cfg, kernel, a, p.g);
+    count_launch();
+    return e;
+}
+
+}  // namespace
+
+// Largest rows-per-thread (fewest idle threads first) whose slabs fit the shared memory of some cluster size.
+bool adj_cluster_config(const Plan &p, ClusterConfig *cfg)
+{
+    int max_smem = 0;
+    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device) != cudaSuccess) return false;
+    ClusterConfig best;
+    bool found = false;
+    ClusterConfig c;
+    // prefer the configuration with the smallest cluster (most work per barrier), ties -> more threads
+    if (adj_config_rmax<7>(p, max_smem, &c)) { best = c; found = true; }
+    if (adj_config_rmax<5>(p, max_smem, &c) && (!found || c.C < best.C)) { best = c; found = true; }
+    if (adj_config_rmax<10>(p, max_smem, &c) && (!found || c.C < best.C)) { best = c; found = true; }
+    if (found) *cfg = best;
+    return found;
+}
+
+cudaError_t launch_adj_cluster(const Plan &p, const ClusterConfig &cc, ClusterAdjArgs a, cudaStream_t st)
+{
+#define RD_DISPATCH(R)                                                               \
+    switch (p.g.pitch) {                                                             \
+        case 312: return launch_adj_cluster_t<R, 312>(p, cc, a, st);                 \
+        case 432: return launch_adj_cluster_t<R, 432>(p, cc, a, st);                 \
+        default: return launch_adj_cluster_t<R, 0>(p, cc, a, st);                    \
+    }
+    switch (cc.rmax) {
+        case 5: RD_DISPATCH(5)
+        case 7: RD_DISPATCH(7)
+        default: RD_DISPATCH(10)
+    }
+#undef RD_DISPATCH
+}
+
+}  // namespace rdfwi

@@ -18,7 +18,8 @@ __device__ __forceinline__ int sponge_index(int i, int n, int nbc)
 }
 
 // tmp[b][iz][x] = sum over the padded rows that replicate model row iz
-__global__ void __launch_bounds__(kThreads) k_fold_rows(const float *__restrict__ Ga, Grid g, float *__restrict__ tmp)
+__global__ void __launch_bounds__(kThreads) k_fold_rows(const float *__restrict__ Ga, Grid g, int planes,
+                                                        float *__restrict__ tmp)
 {
     const int b = blockIdx.y;
     const int i = blockIdx.x * kThreads + threadIdx.x;
@@ -26,9 +27,11 @@ __global__ void __launch_bounds__(kThreads) k_fold_rows(const float *__restrict_
     const int iz = i / g.nxp, x = i - iz * g.nxp;
     const int zlo = iz == 0 ? 0 : iz + g.nbc;
     const int zhi = iz == g.nz - 1 ? g.nzp - 1 : iz + g.nbc;
-    const float *src = Ga + (size_t)b * g.level + x;
     float acc = 0.0f;
-    for (int z = zlo; z <= zhi; ++z) acc += src[(size_t)z * g.pitch];
+    for (int s = 0; s < planes; ++s) {  // fixed order over the shots of the model: deterministic
+        const float *src = Ga + ((size_t)b * planes + s) * g.level + x;
+        for (int z = zlo; z <= zhi; ++z) acc += src[(size_t)z * g.pitch];
+    }
     tmp[(size_t)b * g.nz * g.nxp + i] = acc;
 }
 
@@ -51,10 +54,10 @@ __global__ void __launch_bounds__(kThreads) k_fold_cols(const float *__restrict_
 
 // partial sums of Gk * d(kappa dt)/d(velmin) over the sponge cells of one model (double accumulation)
 __global__ void __launch_bounds__(kThreads) k_velmin_partial(const float *__restrict__ Gk, const float *__restrict__ dkap,
-                                                             Grid g, double *__restrict__ part)
+                                                             Grid g, int planes, double *__restrict__ part)
 {
     const int b = blockIdx.y;
-    const float *src = Gk + (size_t)b * g.level;
+    const float *src = Gk + (size_t)b * planes * g.level;
     double acc = 0.0;
     const int n = g.nzp * g.nxp;
     for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
@@ -62,7 +65,11 @@ __global__ void __launch_bounds__(kThreads) k_velmin_partial(const float *__rest
         const int kx = sponge_index(x, g.nxp, g.nbc);
         const int kz = sponge_index(z, g.nzp, g.nbc);
         const int k = kx >= 0 ? kx : kz;
-        if (k >= 0) acc += (double)(src[(size_t)z * g.pitch + x] * dkap[k]);
+        if (k >= 0) {
+            float gk = 0.0f;
+            for (int s = 0; s < planes; ++s) gk += src[(size_t)s * g.level + (size_t)z * g.pitch + x];
+            acc += (double)(gk * dkap[k]);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -98,16 +105,15 @@ __global__ void k_finish(const double *__restrict__ part, int nparts, const floa
 }  // namespace
 
 cudaError_t launch_gradient_epilogue(const Plan &p, const float *v, int B, const float *Ga, const float *Gk,
-                                     const float *Gb, const float *velmin, const int *argmin, float *fold_tmp,
+                                     const float *Gb, int planes, const int *argmin, float *fold_tmp,
                                      double *vel_part, float *grad_v, cudaStream_t st)
 {
-    (void)velmin;
     const Grid &g = p.g;
-    k_fold_rows<<<dim3((g.nz * g.nxp + kThreads - 1) / kThreads, B), kThreads, 0, st>>>(Ga, g, fold_tmp);
+    k_fold_rows<<<dim3((g.nz * g.nxp + kThreads - 1) / kThreads, B), kThreads, 0, st>>>(Ga, g, planes, fold_tmp);
     count_launch();
     k_fold_cols<<<dim3((g.nz * g.nx + kThreads - 1) / kThreads, B), kThreads, 0, st>>>(fold_tmp, v, g, p.dt_f, p.dx_f, grad_v);
     count_launch();
-    k_velmin_partial<<<dim3(kMinBlocks, B), kThreads, 0, st>>>(Gk, p.d_dkap, g, vel_part);
+    k_velmin_partial<<<dim3(kMinBlocks, B), kThreads, 0, st>>>(Gk, p.d_dkap, g, planes, vel_part);
     count_launch();
     k_finish<<<(B + 63) / 64, 64, 0, st>>>(vel_part, kMinBlocks, Gb, v, p.d_isx, argmin, g, p.dt_f, B, grad_v);
     count_launch();

@@ -70,6 +70,7 @@ struct Workspace {
     size_t bytes = 0;
     size_t chunk_level = 0;  // floats of one level of a full chunk
     int nb = 0;
+    int g_planes = 1;
 };
 
 Workspace carve(const Plan &p, int B, void *base)
@@ -93,8 +94,10 @@ Workspace carve(const Plan &p, int B, void *base)
     w.minpart = (float *)take((size_t)B * kMinBlocks * 2 * 4);
     w.fields = (float *)take(3 * w.chunk_level * 4);
     w.zero = (float *)take(w.chunk_level * 4);
-    w.Ga = (float *)take((size_t)B * g.level * 4);
-    w.Gk = (float *)take((size_t)B * g.level * 4);
+    ClusterConfig acc;
+    w.g_planes = (p.engine != 1 && adj_cluster_config(p, &acc)) ? g.ns : 1;  // per-shot planes for the cluster adjoint
+    w.Ga = (float *)take((size_t)B * w.g_planes * g.level * 4);
+    w.Gk = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gb = (float *)take((size_t)B * g.ns * 4);
     w.fold_tmp = (float *)take((size_t)B * g.nz * g.nxp * 4);
     w.vel_part = (double *)take((size_t)B * kMinBlocks * 8);
@@ -233,6 +236,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "use_graph") { p->use_graph = value != 0; }
     else if (k == "engine") { if (value < 0 || value > 2) goto bad; p->engine = (int)value; }
     else if (k == "cluster_size") { if (value < 0 || value > 8) goto bad; p->cluster_size = (int)value; }
+    else if (k == "adj_cluster_size") { if (value < 0 || value > 8) goto bad; p->adj_cluster_size = (int)value; }
     else { set_error("unknown option " + k); return RDFWI_EINVAL; }
     return RDFWI_OK;
 bad:
@@ -252,6 +256,7 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
     else if (k == "engine") *out = p->engine;
     else if (k == "cluster_size") *out = p->cluster_size;
     else if (k == "cluster_size_used") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cc.C : 0; }
+    else if (k == "adj_cluster_size_used") { ClusterConfig cc; *out = adj_cluster_config(*p, &cc) ? cc.C : 0; }
     else if (k == "pitch") *out = p->g.pitch;
     else if (k == "nzp") *out = p->g.nzp;
     else if (k == "nxp") *out = p->g.nxp;
@@ -371,12 +376,24 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     t_launches = 0;
     Workspace w = carve(p, B, ws);
     RD_CUDA(launch_coefficients(p, v, B, w.alpha, w.kap, w.velmin, w.argmin, w.beta_src, w.minpart, st));
-    RD_CUDA(cudaMemsetAsync(w.zero, 0, w.chunk_level * sizeof(float), st));
-    RD_CUDA(cudaMemsetAsync(w.Ga, 0, (size_t)B * g.level * sizeof(float), st));
-    RD_CUDA(cudaMemsetAsync(w.Gk, 0, (size_t)B * g.level * sizeof(float), st));
-    RD_CUDA(cudaMemsetAsync(w.Gb, 0, (size_t)B * g.ns * sizeof(float), st));
     const float *hist = static_cast<const float *>(history);
     const int nt = p.nt;
+    RD_CUDA(cudaMemsetAsync(w.Gb, 0, (size_t)B * g.ns * sizeof(float), st));
+    ClusterConfig cc;
+    if (w.g_planes > 1 && adj_cluster_config(p, &cc)) {
+        // cluster-resident reverse-time loop: one launch for all shots and all levels
+        ClusterAdjArgs a{};
+        a.alpha = w.alpha; a.kap = w.kap; a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
+        a.wavelet = p.d_wavelet; a.cot = cot; a.hist = hist; a.Ga = w.Ga; a.Gk = w.Gk; a.Gb = w.Gb;
+        a.nshots = B * g.ns; a.nt = nt; a.st = p.st;
+        RD_CUDA(launch_adj_cluster(p, cc, a, st));
+        RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
+        return RDFWI_OK;
+    }
+    if (p.engine == 2) { set_error("engine=2 (cluster-resident) requested but the adjoint slabs do not fit a cluster"); return RDFWI_EINVAL; }
+    RD_CUDA(cudaMemsetAsync(w.zero, 0, w.chunk_level * sizeof(float), st));
+    RD_CUDA(cudaMemsetAsync(w.Ga, 0, (size_t)B * w.g_planes * g.level * sizeof(float), st));
+    RD_CUDA(cudaMemsetAsync(w.Gk, 0, (size_t)B * w.g_planes * g.level * sizeof(float), st));
 
     for (int b0 = 0; b0 < B; b0 += w.nb) {
         const int nb = std::min(w.nb, B - b0);
@@ -404,7 +421,8 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
             launch_adj_step(p, a, nb, st);
         }
     }
-    RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.velmin, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
+    // (when g_planes > 1 but the per-level engine ran, only plane 0 of each model was accumulated into)
+    RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, 1, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
     return RDFWI_OK;
 }
 

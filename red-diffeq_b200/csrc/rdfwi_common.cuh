@@ -61,6 +61,7 @@ struct Plan {
     int adj_rows_per_thread = 1;
     int engine = 0;         // 0 = auto, 1 = per-level kernels, 2 = cluster-resident time loop
     int cluster_size = 0;   // 0 = smallest cluster that fits
+    int adj_cluster_size = 0;
 };
 
 // Cluster-resident forward time loop (kernels_cluster.cu).
@@ -78,12 +79,30 @@ struct ClusterFwdArgs {
     int slabrows, ngroups;  // filled by launch_fwd_cluster from the ClusterConfig
 };
 
+// Cluster-resident reverse-time loop (kernels_cluster_adj.cu).
+struct ClusterAdjArgs {
+    const float *alpha;    // (B, nzp, pitch)
+    const float *kap;      // (B, nbc+1)
+    const int *isx;
+    const int *rec_ptr;
+    const int *rec_idx;
+    const float *wavelet;  // (nt) device
+    const float *cot;      // (B*ns, nt_out, nrec)
+    const float *hist;     // [shot][t][z][x], t = 0..nt-2
+    float *Ga;             // (B*ns, nzp, pitch) per-shot imaging sums (already divided by alpha)
+    float *Gk;             // (B*ns, nzp, pitch)
+    float *Gb;             // (B*ns)
+    int nshots, nt, st;
+    int slabrows, ngroups;  // filled by the launcher from the ClusterConfig
+};
+
 struct ClusterConfig {
     int C = 0;        // CTAs per cluster = row slabs per shot
     int maxrows = 0;  // rows of the largest slab
     int ngroups = 0;  // row groups per CTA (threads = ngroups * q4), kClusterRowsMax rows per thread
     int slabrows = 0; // ngroups * kClusterRowsMax >= maxrows (rows allocated per buffer, halos excluded)
     size_t smem = 0;  // dynamic shared memory per CTA
+    int rmax = 0;     // rows per thread (template instantiation) of the adjoint kernel
 };
 
 // Pointers of one step launch (forward).
@@ -134,9 +153,12 @@ cudaError_t launch_adj_step(const Plan &p, const AdjArgs &a, int nb, cudaStream_
 // kernels_cluster.cu
 bool cluster_config(const Plan &p, ClusterConfig *cfg);
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st);
-// kernels_epilogue.cu
+// kernels_cluster_adj.cu
+bool adj_cluster_config(const Plan &p, ClusterConfig *cfg);
+cudaError_t launch_adj_cluster(const Plan &p, const ClusterConfig &cc, ClusterAdjArgs a, cudaStream_t st);
+// kernels_epilogue.cu  (planes = imaging planes per model: 1 for the per-level engine, ns for the cluster engine)
 cudaError_t launch_gradient_epilogue(const Plan &p, const float *v, int B, const float *Ga, const float *Gk,
-                                     const float *Gb, const float *velmin, const int *argmin, float *fold_tmp,
+                                     const float *Gb, int planes, const int *argmin, float *fold_tmp,
                                      double *vel_part, float *grad_v, cudaStream_t st);
 
 }  // namespace rdfwi
