@@ -64,6 +64,25 @@ struct SweepThread {
     int src_lr, rec_lr;
 };
 
+// asynchronous float4 store into another CTA's shared memory; completes 16 bytes on that CTA's mbarrier
+// (local_ptr / local_bar are this CTA's addresses of the same objects: all CTAs share one smem layout)
+__device__ __forceinline__ void st_async_v4(const float *local_ptr, const uint64_t *local_bar, uint32_t cta, float4 v)
+{
+    uint32_t raddr, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_ptr)), "r"(cta));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar)), "r"(cta));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar)
+                 : "memory");
+}
+
+struct HaloPush {             // per thread
+    bool early;               // this thread sends its first two marching rows from inside the sweep
+    int dst;                  // float offset (inside the written buffer) of the neighbour's halo row for marching row 0
+    uint32_t cta;             // receiving CTA
+    int bar;                  // 0 = the receiver's "top halo" barrier, 1 = its "bottom halo" barrier
+};
+
 // ---- mbarrier + bulk load (global -> shared), used to stream the forward history into the adjoint
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {

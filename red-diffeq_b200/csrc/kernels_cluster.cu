@@ -19,48 +19,59 @@ namespace rdfwi {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ forward
-// Hot loop notes (from the ncu captures under profiles/): the kernel is issue-bound, so the row sweep is
-// kept free of branches and address arithmetic:
+// Hot loop notes (from the ncu captures under profiles/): the kernel is issue-bound and, in its first
+// versions, lost half of its cycles at a per-level barrier.cluster (MEMBAR.ALL.GPU + skew).  Hence:
 //   * PITCH is a template parameter for the production grids (0 = runtime pitch), so every row offset is
 //     an immediate of the LDS/STS instruction;
-//   * the time loop is unrolled by two, which makes "which buffer holds p_{t-1}" a compile-time role;
-//   * rows a thread does not own are still computed (from in-bounds garbage) and only their store is
-//     predicated;
-//   * source injection, receiver sampling and the halo pushes run in a short epilogue, executed by the
-//     threads that own those rows.
+//   * rows a thread does not own are still computed (from in-bounds garbage), only their store is predicated;
+//   * source injection and receiver sampling run in a short epilogue, executed by the owner threads;
+//   * there is NO cluster-wide barrier inside the time loop.  Halo rows travel as st.async stores that
+//     complete transaction bytes on an mbarrier of the receiving CTA.  The row group that owns the top
+//     rows marches downwards and the one that owns the bottom rows marches upwards, so both produce the
+//     rows their neighbours need in their first two iterations and send them at once; the consumers wait
+//     for them only at the start of the next level, a whole sweep later.  The write-after-read hazard on
+//     a halo buffer is covered by the data dependency itself: a CTA sends level-t edge rows only after it
+//     received (and read) its neighbour's level t-1 rows, which that neighbour sent after reading its own
+//     halo.  Inside a CTA one __syncthreads per level orders the row groups.
+//   * two sweep instantiations (down / up) still fit the instruction cache; four (x two buffer roles) did
+//     not (ncu: stall_no_instruction), so buffer roles are runtime base pointers.
 
-template <int RMAX, int PITCH>
+template <int RMAX, int PITCH, int DIR>
 __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cur, const int prv, const int kap_off,
-                                          const int pitch_rt, const SweepThread &th, const float4 (&al)[RMAX],
-                                          const float (&kapx)[4])
+                                          const int pitch_rt, const int l0, const SweepThread &th,
+                                          const float4 (&al)[RMAX], const float (&kapx)[4], const HaloPush &hp,
+                                          const uint64_t *push_bar, const bool push_now)
 {
     const int pitch = PITCH > 0 ? PITCH : pitch_rt;
+    const int P = DIR * pitch;                                     // signed row step in marching order
     const float c2 = 4.0f / 3.0f, c3 = -1.0f / 12.0f;
-    const float *cb = smem + cur + (2 + th.lac) * pitch + th.x;  // row la of p_{t-1}, this thread's float4
-    float *pb = smem + prv + (2 + th.lac) * pitch + th.x;        // row la of p_{t-2}; p_t goes there
-    const float *eLp = smem + cur + (2 + th.lac) * pitch + th.eL;
-    const float *eRp = smem + cur + (2 + th.lac) * pitch + th.eR;
-    const float *kz = smem + kap_off + th.lac;
+    const float *cb = smem + cur + (2 + l0) * pitch + th.x;        // row l0 of p_{t-1}, this thread's float4
+    float *pb = smem + prv + (2 + l0) * pitch + th.x;              // row l0 of p_{t-2}; p_t goes there
+    const float *eLp = smem + cur + (2 + l0) * pitch + th.eL;
+    const float *eRp = smem + cur + (2 + l0) * pitch + th.eR;
+    const float *kz = smem + kap_off + l0;
+    const float *push_dst = smem + prv + hp.dst + th.x;
 
-    float4 w0 = ld4(cb - 2 * pitch), w1 = ld4(cb - pitch), w2 = ld4(cb), w3 = ld4(cb + pitch);
+    float4 w0 = ld4(cb - 2 * P), w1 = ld4(cb - P), w2 = ld4(cb), w3 = ld4(cb + P);
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
-        const float4 w4 = ld4(cb + (r + 2) * pitch);
-        const float4 old = ld4(pb + r * pitch);
-        const float kapz = kz[r];
+        const float4 w4 = ld4(cb + (r + 2) * P);
+        const float4 old = ld4(pb + r * P);
+        const float kapz = kz[DIR * r];
         // x-neighbours outside the float4 come from the adjacent lanes' centre vectors
         float l2 = __shfl_up_sync(0xffffffffu, w2.z, 1);
         float l1 = __shfl_up_sync(0xffffffffu, w2.w, 1);
         float r0 = __shfl_down_sync(0xffffffffu, w2.x, 1);
         float r1 = __shfl_down_sync(0xffffffffu, w2.y, 1);
-        if (th.edgeL) { l2 = eLp[r * pitch]; l1 = eLp[r * pitch + 1]; }
-        if (th.edgeR) { r0 = eRp[r * pitch]; r1 = eRp[r * pitch + 1]; }
+        if (th.edgeL) { l2 = eLp[r * P]; l1 = eLp[r * P + 1]; }
+        if (th.edgeR) { r0 = eRp[r * P]; r1 = eRp[r * P + 1]; }
         const float e[8] = {l2, l1, w2.x, w2.y, w2.z, w2.w, r0, r1};
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float kp = th.colsp[j] ? kapx[j] : kapz;  // columns override rows (solvers/pde.py:50-51)
             const float alj = lane(al[r], j);
+            // fp32 addition is commutative, so marching upwards (w1 = row below) gives the same bits as (:79)
             const float s1 = __fadd_rn(__fadd_rn(__fadd_rn(lane(w1, j), lane(w3, j)), e[j + 1]), e[j + 3]);
             const float s2 = __fadd_rn(__fadd_rn(__fadd_rn(lane(w0, j), lane(w4, j)), e[j]), e[j + 4]);
             const float lap = __fadd_rn(__fmul_rn(c2, s1), __fmul_rn(c3, s2));
@@ -68,7 +79,10 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             const float t2 = __fsub_rn(1.0f, kp);                                     // temp2 (:70)
             o[j] = __fadd_rn(__fsub_rn(__fmul_rn(t1, e[j + 2]), __fmul_rn(t2, lane(old, j))), __fmul_rn(alj, lap));
         }
-        if (th.la + r < th.lb) st4(pb + r * pitch, make_float4(o[0], o[1], o[2], o[3]));
+        const int lr = l0 + DIR * r;
+        const float4 out = make_float4(o[0], o[1], o[2], o[3]);
+        if (lr >= th.la && lr < th.lb) st4(pb + r * P, out);
+        if (r < 2 && push_now) st_async_v4(push_dst + r * P, push_bar, hp.cta, out);  // edge rows leave at once
         w0 = w1; w1 = w2; w2 = w3; w3 = w4;
     }
 }
@@ -90,6 +104,14 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     const int pitch = PITCH > 0 ? PITCH : g.pitch;
     const int slab = (a.slabrows + 4) * pitch;  // floats per buffer: 2 halo rows, slab rows, 2 halo rows
     const int kap_off = 2 * slab;               // per-row sponge value of the CTA's rows (slabrows floats)
+    // halo mbarriers: [buffer][top|bottom]; same offsets in every CTA of the cluster
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ((kap_off + a.slabrows + 3) & ~3));
+    // small read-only tables staged once per kernel so the epilogue never waits on global memory:
+    // receiver CSR (columns -> receiver slots) and, when it fits, the wavelet
+    int *s_rec_ptr = reinterpret_cast<int *>(bars + 4);
+    int *s_rec_idx = s_rec_ptr + g.nxp + 1;
+    float *s_wav = reinterpret_cast<float *>(s_rec_idx + g.nrec);
+    const bool wav_in_smem = a.wav_smem != 0;
 
     const int tid = threadIdx.x, lane_id = tid & 31;
     const int grp = tid / g.q4, col = tid - grp * g.q4;
@@ -99,7 +121,6 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     th.x = col * 4;
     th.la = grp * RMAX;
     th.lb = !active ? th.la : (th.la + RMAX < nrows ? th.la + RMAX : nrows);
-    th.lac = active ? th.la : 0;
     th.edgeL = lane_id == 0 || col == 0;
     th.edgeR = lane_id == 31 || col == g.q4 - 1;
     th.eL = col == 0 ? g.nxp - 2 : th.x - 2;
@@ -113,10 +134,57 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     // rows this thread must handle in the epilogue (local row index, or -1)
     th.src_lr = (g.isz - r0 >= th.la && g.isz - r0 < th.lb) ? g.isz - r0 : -1;
     th.rec_lr = (g.igz - r0 >= th.la && g.igz - r0 < th.lb) ? g.igz - r0 : -1;
+    // Warps holding lanes of the group that owns the CTA's last row march upwards from that row, all others
+    // downwards from their first row; idle lanes shadow the last group (their stores are predicated off).
+    const int last_grp = (nrows - 1) / RMAX;
+    const bool rev = __any_sync(0xffffffffu, active && grp == last_grp && last_grp > 0) != 0;
+    const int la_eff = active ? th.la : last_grp * RMAX;
+    const int lb_eff = active ? th.lb : nrows;
+    const int l0 = rev ? (lb_eff > la_eff ? lb_eff - 1 : la_eff) : la_eff;  // first row in marching order
+    th.lac = l0;
+    // which halos the warp reads during a sweep (rows < 0 / rows nrows, nrows+1)
+    bool rd_top, rd_bot;
+    {
+        const int lo = rev ? l0 - (RMAX + 1) : l0 - 2, hi = rev ? l0 + 2 : l0 + RMAX + 1;
+        rd_top = __any_sync(0xffffffffu, lo < 0) != 0;
+        rd_bot = __any_sync(0xffffffffu, hi >= nrows && lo < nrows + 2) != 0;
+    }
+    // early halo pushes: the CTA's first / last two rows are marching rows 0,1 of their owner threads --
+    // unless the source row is one of them (it is patched in the epilogue, after which it is sent)
+    const bool src_on_edge = g.isz - r0 >= 0 && g.isz - r0 < nrows && (g.isz - r0 < 2 || g.isz - r0 >= nrows - 2);
+    HaloPush hp;
+    hp.early = false; hp.dst = 0; hp.cta = 0; hp.bar = 0;
+    if (active && !src_on_edge) {
+        if (!rev && th.la == 0 && th.lb >= 2) {          // rows 0,1 -> bottom halo of the CTA above
+            hp.early = true; hp.dst = (2 + nrows_up) * pitch; hp.cta = (uint32_t)up; hp.bar = 1;
+        } else if (rev && th.lb == nrows && th.lb - th.la >= 2) {  // rows nrows-1, nrows-2 -> top halo of the CTA below
+            hp.early = true; hp.dst = pitch; hp.cta = (uint32_t)dn; hp.bar = 0;
+        }
+    }
+    // edge rows this thread owns but does not send early (bit h: top row h; bit 2+h: row nrows-2+h)
+    int late = 0;
+    for (int h = 0; h < 2; ++h) {
+        if (h >= th.la && h < th.lb && !(hp.early && hp.bar == 1)) late |= 1 << h;
+        const int rb = nrows - 2 + h;
+        if (rb >= th.la && rb < th.lb && !(hp.early && hp.bar == 0)) late |= 4 << h;
+    }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t hist_shot = (size_t)(a.nt - 1) * g.level;
+    const uint32_t halo_bytes = (uint32_t)(2 * pitch * sizeof(float));
+    // halo phases consumed per shot from buffer 1 (levels 1,3,..) and buffer 0 (levels 2,4,..)
+    const int uses1 = a.nt / 2, uses0 = (a.nt - 1) / 2;
 
-    for (int shot = cid; shot < a.nshots; shot += ncl) {
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+    }
+    for (int i = tid; i <= g.nxp; i += kClusterThreads) s_rec_ptr[i] = a.rec_ptr[i];
+    for (int i = tid; i < g.nrec; i += kClusterThreads) s_rec_idx[i] = a.rec_idx[i];
+    if (wav_in_smem)
+        for (int i = tid; i < a.nt; i += kClusterThreads) s_wav[i] = a.wavelet[i];
+    __syncthreads();
+
+    int shot_iter = 0;
+    for (int shot = cid; shot < a.nshots; shot += ncl, ++shot_iter) {
         const int b = shot / g.ns, s = shot - b * g.ns;
         // p_{-1} = p_{-2} = 0 (halo rows included); sponge tables of this model
         for (int i = tid; i < 2 * slab; i += kClusterThreads) smem[i] = 0.0f;
@@ -125,10 +193,12 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
             const int kz = sponge_index(r0 + i, g.nzp, g.nbc);
             smem[kap_off + i] = (i < nrows && kz >= 0) ? kap_b[kz] : 0.0f;
         }
-        float4 al[RMAX];
+        float4 al[RMAX];  // alpha of the thread's rows, in marching order
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-            al[r] = (th.la + r < th.lb) ? ld4(a.alpha + (size_t)b * g.level + (size_t)(r0 + th.la + r) * pitch + th.x) : zero4;
+        for (int r = 0; r < RMAX; ++r) {
+            const int lrow = rev ? l0 - r : l0 + r;
+            al[r] = (lrow >= th.la && lrow < th.lb) ? ld4(a.alpha + (size_t)b * g.level + (size_t)(r0 + lrow) * pitch + th.x) : zero4;
+        }
         float kapx[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -141,15 +211,32 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
         for (int j = 0; j < 4; ++j) src_mask |= (th.src_lr >= 0 && xc[j] == xs) ? (1 << j) : 0;
         const float bsrc = a.beta_src[shot];
         __syncthreads();
-        cluster_sync_all();  // every CTA of the cluster has cleared its buffers before halos are pushed
+        cluster_sync_all();  // shot boundary: every CTA has finished the previous shot and cleared its buffers
 
         // one time level: p_{t-1} in buffer `cur`, p_{t-2} in `prv`, p_t overwrites p_{t-2}
         auto level = [&](const int t, const int cur, const int prv) {
+            const int cbuf = cur == 0 ? 0 : 1, pbuf = 1 - cbuf;
+            uint64_t *bar_top = bars + 2 * cbuf, *bar_bot = bars + 2 * cbuf + 1;
+            const bool sends = t + 1 < a.nt;  // the last level of a shot has no consumer
+            if (t >= 1) {
+                // the halos of `cur` were sent by the neighbours early in level t-1 (t = 0: zero initial state)
+                const uint32_t parity = (uint32_t)((shot_iter * (cbuf ? uses1 : uses0) + (t - 1) / 2) & 1);
+                if (tid == 0) {
+                    mbar_expect_tx(bar_top, halo_bytes);
+                    mbar_expect_tx(bar_bot, halo_bytes);
+                }
+                if (warp_active) {
+                    if (rd_top) mbar_wait(bar_top, parity);
+                    if (rd_bot) mbar_wait(bar_bot, parity);
+                }
+            }
             const int p0 = prv + 2 * pitch + th.x;
             if (warp_active) {
-                fwd_sweep<RMAX, PITCH>(smem, cur, prv, kap_off, pitch, th, al, kapx);
+                const uint64_t *push_bar = bars + 2 * pbuf + hp.bar;  // barrier of the buffer written now, at the receiver
+                if (rev) fwd_sweep<RMAX, PITCH, -1>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
+                else fwd_sweep<RMAX, PITCH, 1>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
                 if (src_mask != 0) {  // p[src] += beta_dt[src] * wavelet[t]   (solvers/pde.py:80-81)
-                    const float src_add = __fmul_rn(bsrc, a.wavelet[t]);
+                    const float src_add = __fmul_rn(bsrc, wav_in_smem ? s_wav[t] : a.wavelet[t]);
                     float4 v = ld4(smem + p0 + th.src_lr * pitch);
                     if (src_mask & 1) v.x = __fadd_rn(v.x, src_add);
                     if (src_mask & 2) v.y = __fadd_rn(v.y, src_add);
@@ -163,35 +250,34 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         if (th.x + j < g.nxp)
-                            for (int k = a.rec_ptr[th.x + j]; k < a.rec_ptr[th.x + j + 1]; ++k) seis_t[a.rec_idx[k]] = lane(v, j);
+                            for (int k = s_rec_ptr[th.x + j]; k < s_rec_ptr[th.x + j + 1]; ++k) seis_t[s_rec_idx[k]] = lane(v, j);
                 }
-                // halo rows of the neighbours (periodic ring over the cluster, like torch.roll in z)
-                if (th.la < 2)
-                    for (int h = th.la; h < 2 && h < th.lb; ++h)
-                        st_cluster_v4(smem + prv + (2 + nrows_up + h) * pitch + th.x, (uint32_t)up, ld4(smem + p0 + h * pitch));
-                if (th.lb > nrows - 2)
-                    for (int h = (th.la > nrows - 2 ? th.la : nrows - 2); h < th.lb; ++h)
-                        st_cluster_v4(smem + prv + (h - (nrows - 2)) * pitch + th.x, (uint32_t)dn, ld4(smem + p0 + h * pitch));
+                if (late != 0 && sends) {  // edge rows that could not leave from inside the sweep
+                    for (int h = 0; h < 2; ++h) {
+                        if (late & (1 << h))
+                            st_async_v4(smem + prv + (2 + nrows_up + h) * pitch + th.x, bars + 2 * pbuf + 1, (uint32_t)up,
+                                        ld4(smem + p0 + h * pitch));
+                        if (late & (4 << h))
+                            st_async_v4(smem + prv + h * pitch + th.x, bars + 2 * pbuf, (uint32_t)dn,
+                                        ld4(smem + p0 + (nrows - 2 + h) * pitch));
+                    }
+                }
             }
             if (a.hist != nullptr) {
                 fence_proxy_async();             // slab writes -> visible to the bulk-copy engine
                 if (tid == 0) bulk_wait_read();  // the copy of the previous level has finished reading its buffer
             }
-            cluster_sync_all();
+            __syncthreads();                     // rows of level t are complete CTA-wide
             if (a.hist != nullptr && tid == 0 && t <= a.nt - 2)
                 bulk_store(a.hist + (size_t)shot * hist_shot + (size_t)t * g.level + (size_t)r0 * pitch,
                            smem + prv + 2 * pitch, (uint32_t)(nrows * pitch * sizeof(float)));
         };
-        int t = 0;
-        for (; t + 1 < a.nt; t += 2) {
-            level(t, 0, slab);
-            level(t + 1, slab, 0);
-        }
-        if (t < a.nt) level(t, 0, slab);
+        for (int t = 0, cur = 0; t < a.nt; ++t, cur = slab - cur) level(t, cur, slab - cur);
         if (a.hist != nullptr && tid == 0) bulk_wait_read();
         __syncthreads();
     }
     if (tid == 0) bulk_wait_all();
+    cluster_sync_all();  // no CTA exits while a neighbour may still address its shared memory
 }
 
 }  // namespace
@@ -210,8 +296,10 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg)
         const int ngroups = (maxrows + kClusterRowsMax - 1) / kClusterRowsMax;  // each thread marches kClusterRowsMax rows
         if (ngroups > groups_max) continue;
         const int slabrows = ngroups * kClusterRowsMax;  // >= maxrows: rows past the slab are computed but never stored
-        const size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 8) * sizeof(float);
+        size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + g.nxp + 1 + g.nrec) * sizeof(float);
         if (smem > (size_t)max_smem) continue;
+        cfg->wav_smem = smem + (size_t)p.nt * sizeof(float) <= (size_t)max_smem;
+        if (cfg->wav_smem) smem += (size_t)p.nt * sizeof(float);
         cfg->C = C; cfg->maxrows = maxrows; cfg->ngroups = ngroups; cfg->slabrows = slabrows; cfg->smem = smem;
         return true;
     }
@@ -224,7 +312,7 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
     auto kernel = k_fwd_cluster<kClusterRowsMax, PITCH>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
     if (e != cudaSuccess) return e;
-    a.slabrows = cc.slabrows; a.ngroups = cc.ngroups;
+    a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
 
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];

@@ -19,41 +19,50 @@
 namespace rdfwi {
 namespace {
 
-// u_t over the thread's rows: same structure as fwd_sweep, FMA contraction allowed (no bit-parity
-// requirement on the adjoint), alpha read from its shared-memory slab.
-template <int RMAX, int PITCH>
-__device__ __forceinline__ void adj_sweep(float *__restrict__ smem, const int cur, const int prv, const int al_off,
-                                          const int kap_off, const int pitch_rt, const SweepThread &th,
-                                          const float (&kapx)[4])
+// u_t over the thread's rows: same structure as fwd_sweep (kernels_cluster.cu) including the early halo
+// sends, but FMA contraction is allowed (no bit-parity requirement on the adjoint) and alpha is streamed
+// from global memory (L2-resident: one plane per model), because the imaging sums own the registers.
+template <int RMAX, int PITCH, int DIR>
+__device__ __forceinline__ void adj_sweep(float *__restrict__ smem, const int cur, const int prv, const int kap_off,
+                                          const int pitch_rt, const int l0, const SweepThread &th,
+                                          const float *__restrict__ alpha_row0, const float (&kapx)[4], const HaloPush &hp,
+                                          const uint64_t *push_bar, const bool push_now)
 {
     const int pitch = PITCH > 0 ? PITCH : pitch_rt;
+    const int P = DIR * pitch;
     const float c2 = 4.0f / 3.0f, c3 = -1.0f / 12.0f;
-    const float *cb = smem + cur + (2 + th.lac) * pitch + th.x;
-    float *pb = smem + prv + (2 + th.lac) * pitch + th.x;
-    const float *ab = smem + al_off + th.lac * pitch + th.x;
-    const float *eLp = smem + cur + (2 + th.lac) * pitch + th.eL;
-    const float *eRp = smem + cur + (2 + th.lac) * pitch + th.eR;
-    const float *kz = smem + kap_off + th.lac;
+    const float *cb = smem + cur + (2 + l0) * pitch + th.x;
+    float *pb = smem + prv + (2 + l0) * pitch + th.x;
+    const float *eLp = smem + cur + (2 + l0) * pitch + th.eL;
+    const float *eRp = smem + cur + (2 + l0) * pitch + th.eR;
+    const float *kz = smem + kap_off + l0;
+    const float *push_dst = smem + prv + hp.dst + th.x;
+    const float *ab = alpha_row0 + (long)l0 * pitch + th.x;  // alpha of row l0 (global)
 
-    float4 w0 = ld4(cb - 2 * pitch), w1 = ld4(cb - pitch), w2 = ld4(cb), w3 = ld4(cb + pitch);
+    float4 alv[RMAX];
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
-        const float4 w4 = ld4(cb + (r + 2) * pitch);
-        const float4 old = ld4(pb + r * pitch);
-        const float4 alv = ld4(ab + r * pitch);
-        const float kapz = kz[r];
+        const int lr = l0 + DIR * r;
+        alv[r] = (lr >= th.la && lr < th.lb) ? __ldg(reinterpret_cast<const float4 *>(ab + r * P)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+    float4 w0 = ld4(cb - 2 * P), w1 = ld4(cb - P), w2 = ld4(cb), w3 = ld4(cb + P);
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+        const float4 w4 = ld4(cb + (r + 2) * P);
+        const float4 old = ld4(pb + r * P);
+        const float kapz = kz[DIR * r];
         float l2 = __shfl_up_sync(0xffffffffu, w2.z, 1);
         float l1 = __shfl_up_sync(0xffffffffu, w2.w, 1);
         float r0 = __shfl_down_sync(0xffffffffu, w2.x, 1);
         float r1 = __shfl_down_sync(0xffffffffu, w2.y, 1);
-        if (th.edgeL) { l2 = eLp[r * pitch]; l1 = eLp[r * pitch + 1]; }
-        if (th.edgeR) { r0 = eRp[r * pitch]; r1 = eRp[r * pitch + 1]; }
+        if (th.edgeL) { l2 = eLp[r * P]; l1 = eLp[r * P + 1]; }
+        if (th.edgeR) { r0 = eRp[r * P]; r1 = eRp[r * P + 1]; }
         const float e[8] = {l2, l1, w2.x, w2.y, w2.z, w2.w, r0, r1};
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float kp = th.colsp[j] ? kapx[j] : kapz;
-            const float alj = lane(alv, j);
+            const float alj = lane(alv[r], j);
             const float s1 = ((lane(w1, j) + lane(w3, j)) + e[j + 1]) + e[j + 3];
             const float s2 = ((lane(w0, j) + lane(w4, j)) + e[j]) + e[j + 4];
             const float lap = c2 * s1 + c3 * s2;
@@ -61,37 +70,42 @@ __device__ __forceinline__ void adj_sweep(float *__restrict__ smem, const int cu
             const float t2 = 1.0f - kp;
             o[j] = (t1 * e[j + 2] - t2 * lane(old, j)) + alj * lap;
         }
-        if (th.la + r < th.lb) st4(pb + r * pitch, make_float4(o[0], o[1], o[2], o[3]));
+        const int lr = l0 + DIR * r;
+        const float4 out = make_float4(o[0], o[1], o[2], o[3]);
+        if (lr >= th.la && lr < th.lb) st4(pb + r * P, out);
+        if (r < 2 && push_now) st_async_v4(push_dst + r * P, push_bar, hp.cta, out);
         w0 = w1; w1 = w2; w2 = w3; w3 = w4;
     }
 }
 
-// imaging sums of one level: Ga += u_t (S-5) p_{t-1},  Gk += (u_{t+1} - u_t) p_{t-1}
-template <int RMAX, int PITCH>
+// imaging sums of one level, rows in the same marching order as the sweep:
+//     Ga += u_t (S-5) p_{t-1},  Gk += (u_{t+1} - u_t) p_{t-1}
+template <int RMAX, int PITCH, int DIR>
 __device__ __forceinline__ void imaging_sweep(const float *__restrict__ smem, const int ucur, const int uprv, const int pbuf,
-                                              const int pitch_rt, const SweepThread &th, float4 (&Ga)[RMAX],
+                                              const int pitch_rt, const int l0, const SweepThread &th, float4 (&Ga)[RMAX],
                                               float4 (&Gk)[RMAX])
 {
     const int pitch = PITCH > 0 ? PITCH : pitch_rt;
+    const int P = DIR * pitch;
     const float c2 = 4.0f / 3.0f, c3 = -1.0f / 12.0f;
-    const float *pb = smem + pbuf + (2 + th.lac) * pitch + th.x;       // p_{t-1}, row la
-    const float *u1b = smem + ucur + (2 + th.lac) * pitch + th.x;      // u_{t+1}
-    const float *utb = smem + uprv + (2 + th.lac) * pitch + th.x;      // u_t (just written by this thread)
-    const float *eLp = smem + pbuf + (2 + th.lac) * pitch + th.eL;
-    const float *eRp = smem + pbuf + (2 + th.lac) * pitch + th.eR;
+    const float *pb = smem + pbuf + (2 + l0) * pitch + th.x;       // p_{t-1}, row l0
+    const float *u1b = smem + ucur + (2 + l0) * pitch + th.x;      // u_{t+1}
+    const float *utb = smem + uprv + (2 + l0) * pitch + th.x;      // u_t (just written by this thread)
+    const float *eLp = smem + pbuf + (2 + l0) * pitch + th.eL;
+    const float *eRp = smem + pbuf + (2 + l0) * pitch + th.eR;
 
-    float4 v0 = ld4(pb - 2 * pitch), v1 = ld4(pb - pitch), v2 = ld4(pb), v3 = ld4(pb + pitch);
+    float4 v0 = ld4(pb - 2 * P), v1 = ld4(pb - P), v2 = ld4(pb), v3 = ld4(pb + P);
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
-        const float4 v4 = ld4(pb + (r + 2) * pitch);
-        const float4 ut = ld4(utb + r * pitch);
-        const float4 u1 = ld4(u1b + r * pitch);
+        const float4 v4 = ld4(pb + (r + 2) * P);
+        const float4 ut = ld4(utb + r * P);
+        const float4 u1 = ld4(u1b + r * P);
         float l2 = __shfl_up_sync(0xffffffffu, v2.z, 1);
         float l1 = __shfl_up_sync(0xffffffffu, v2.w, 1);
         float r0 = __shfl_down_sync(0xffffffffu, v2.x, 1);
         float r1 = __shfl_down_sync(0xffffffffu, v2.y, 1);
-        if (th.edgeL) { l2 = eLp[r * pitch]; l1 = eLp[r * pitch + 1]; }
-        if (th.edgeR) { r0 = eRp[r * pitch]; r1 = eRp[r * pitch + 1]; }
+        if (th.edgeL) { l2 = eLp[r * P]; l1 = eLp[r * P + 1]; }
+        if (th.edgeR) { r0 = eRp[r * P]; r1 = eRp[r * P + 1]; }
         const float e[8] = {l2, l1, v2.x, v2.y, v2.z, v2.w, r0, r1};
         float ga[4] = {Ga[r].x, Ga[r].y, Ga[r].z, Ga[r].w};
         float gk[4] = {Gk[r].x, Gk[r].y, Gk[r].z, Gk[r].w};
@@ -125,11 +139,15 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_adj_cluster(ClusterAdjAr
     const int nrows_up = base + (up < rem ? 1 : 0);
 
     const int pitch = PITCH > 0 ? PITCH : g.pitch;
-    const int slab = (a.slabrows + 4) * pitch;
-    const int pbuf = 2 * slab;                    // forward level t-1 with halo rows
-    const int al_off = 3 * slab;                  // alpha of the CTA's rows
-    const int kap_off = al_off + a.slabrows * pitch;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + ((kap_off + a.slabrows + 3) & ~3));
+    const int slab = (a.slabrows + 4) * pitch;   // u slabs: 2 halo rows, slab rows, 2 halo rows
+    const int pslab0 = 2 * slab;                 // two forward-history slabs (levels t-1 / t-2 in flight)
+    const int kap_off = 4 * slab;
+    // mbarriers: [0..3] u halos [buffer][top|bottom], [4..5] history slabs
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ((kap_off + a.slabrows + 3) & ~3));
+    int *s_rec_ptr = reinterpret_cast<int *>(bars + 6);
+    int *s_rec_idx = s_rec_ptr + g.nxp + 1;
+    float *s_wav = reinterpret_cast<float *>(s_rec_idx + g.nrec);
+    const bool wav_in_smem = a.wav_smem != 0;
 
     const int tid = threadIdx.x, lane_id = tid & 31;
     const int grp = tid / g.q4, col = tid - grp * g.q4;
@@ -139,7 +157,6 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_adj_cluster(ClusterAdjAr
     th.x = col * 4;
     th.la = grp * RMAX;
     th.lb = !active ? th.la : (th.la + RMAX < nrows ? th.la + RMAX : nrows);
-    th.lac = active ? th.la : 0;
     th.edgeL = lane_id == 0 || col == 0;
     th.edgeR = lane_id == 31 || col == g.q4 - 1;
     th.eL = col == 0 ? g.nxp - 2 : th.x - 2;
@@ -152,33 +169,74 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_adj_cluster(ClusterAdjAr
     }
     th.src_lr = (g.isz - r0 >= th.la && g.isz - r0 < th.lb) ? g.isz - r0 : -1;
     th.rec_lr = (g.igz - r0 >= th.la && g.igz - r0 < th.lb) ? g.igz - r0 : -1;
+    // marching directions, halo reads and early sends: as in k_fwd_cluster
+    const int last_grp = (nrows - 1) / RMAX;
+    const bool rev = __any_sync(0xffffffffu, active && grp == last_grp && last_grp > 0) != 0;
+    const int la_eff = active ? th.la : last_grp * RMAX;
+    const int lb_eff = active ? th.lb : nrows;
+    const int l0 = rev ? (lb_eff > la_eff ? lb_eff - 1 : la_eff) : la_eff;
+    th.lac = l0;
+    bool rd_top, rd_bot;
+    {
+        const int lo = rev ? l0 - (RMAX + 1) : l0 - 2, hi = rev ? l0 + 2 : l0 + RMAX + 1;
+        rd_top = __any_sync(0xffffffffu, lo < 0) != 0;
+        rd_bot = __any_sync(0xffffffffu, hi >= nrows && lo < nrows + 2) != 0;
+    }
+    // the receiver row is patched in the epilogue (cotangent injection), so it cannot be sent early
+    const bool rec_on_edge = g.igz - r0 >= 0 && g.igz - r0 < nrows && (g.igz - r0 < 2 || g.igz - r0 >= nrows - 2);
+    HaloPush hp;
+    hp.early = false; hp.dst = 0; hp.cta = 0; hp.bar = 0;
+    if (active && !rec_on_edge) {
+        if (!rev && th.la == 0 && th.lb >= 2) {
+            hp.early = true; hp.dst = (2 + nrows_up) * pitch; hp.cta = (uint32_t)up; hp.bar = 1;
+        } else if (rev && th.lb == nrows && th.lb - th.la >= 2) {
+            hp.early = true; hp.dst = pitch; hp.cta = (uint32_t)dn; hp.bar = 0;
+        }
+    }
+    int late = 0;
+    for (int h = 0; h < 2; ++h) {
+        if (h >= th.la && h < th.lb && !(hp.early && hp.bar == 1)) late |= 1 << h;
+        const int rb = nrows - 2 + h;
+        if (rb >= th.la && rb < th.lb && !(hp.early && hp.bar == 0)) late |= 4 << h;
+    }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t hist_shot = (size_t)(a.nt - 1) * g.level;
+    const uint32_t halo_bytes = (uint32_t)(2 * pitch * sizeof(float));
+    // u-halo phases consumed per shot: reverse level index k = nt-1-t; buffer roles alternate with k
+    const int uses1 = a.nt / 2, uses0 = (a.nt - 1) / 2;
+    // history loads per shot: levels nt-2 .. 0 -> slab (lvl & 1)
+    const int loads1 = (a.nt - 1) / 2, loads0 = a.nt / 2;
 
-    if (tid == 0) mbar_init(mbar, 1);
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) mbar_init(bars + i, 1);
+    }
+    for (int i = tid; i <= g.nxp; i += kClusterThreads) s_rec_ptr[i] = a.rec_ptr[i];
+    for (int i = tid; i < g.nrec; i += kClusterThreads) s_rec_idx[i] = a.rec_idx[i];
+    if (wav_in_smem)
+        for (int i = tid; i < a.nt; i += kClusterThreads) s_wav[i] = a.wavelet[i];
     __syncthreads();
-    uint32_t phase = 0;
 
-    // stream forward level `lvl` (rows r0-2 .. r0+nrows+1, periodic in z) of `shot` into the p slab
+    // stream forward level `lvl` (rows r0-2 .. r0+nrows+1, periodic in z) of `shot` into history slab (lvl & 1)
     auto load_level = [&](const int shot, const int lvl) {
         const float *src = a.hist + (size_t)shot * hist_shot + (size_t)lvl * g.level;
+        float *dst = smem + pslab0 + (lvl & 1) * slab;
+        uint64_t *bar = bars + 4 + (lvl & 1);
         const uint32_t row_b = (uint32_t)(pitch * sizeof(float));
         const int top = r0 - 2 < 0 ? r0 - 2 + g.nzp : r0 - 2;                      // first halo row (wraps for rank 0)
         const int bot = r0 + nrows >= g.nzp ? r0 + nrows - g.nzp : r0 + nrows;     // first row below the slab
-        mbar_expect_tx(mbar, (uint32_t)(nrows + 4) * row_b);
-        bulk_load(smem + pbuf, src + (size_t)top * pitch, 2 * row_b, mbar);
-        bulk_load(smem + pbuf + 2 * pitch, src + (size_t)r0 * pitch, (uint32_t)nrows * row_b, mbar);
-        bulk_load(smem + pbuf + (2 + nrows) * pitch, src + (size_t)bot * pitch, 2 * row_b, mbar);
+        mbar_expect_tx(bar, (uint32_t)(nrows + 4) * row_b);
+        bulk_load(dst, src + (size_t)top * pitch, 2 * row_b, bar);
+        bulk_load(dst + 2 * pitch, src + (size_t)r0 * pitch, (uint32_t)nrows * row_b, bar);
+        bulk_load(dst + (2 + nrows) * pitch, src + (size_t)bot * pitch, 2 * row_b, bar);
     };
 
-    for (int shot = cid; shot < a.nshots; shot += ncl) {
+    int shot_iter = 0;
+    for (int shot = cid; shot < a.nshots; shot += ncl, ++shot_iter) {
         const int b = shot / g.ns, s = shot - b * g.ns;
-        // u_{nt} = u_{nt+1} = 0; alpha slab and sponge tables of this model
+        // u_{nt} = u_{nt+1} = 0; sponge tables of this model
         for (int i = tid; i < 2 * slab; i += kClusterThreads) smem[i] = 0.0f;
         const float *kap_b = a.kap + (size_t)b * (g.nbc + 1);
-        const float *alpha_b = a.alpha + (size_t)b * g.level + (size_t)r0 * pitch;
-        for (int i = tid * 4; i < a.slabrows * pitch; i += kClusterThreads * 4)
-            st4(smem + al_off + i, i < nrows * pitch ? ld4(alpha_b + i) : make_float4(1.f, 1.f, 1.f, 1.f));
+        const float *alpha_row0 = a.alpha + (size_t)b * g.level + (size_t)r0 * pitch;  // alpha of the CTA's row 0
         for (int i = tid; i < a.slabrows; i += kClusterThreads) {
             const int kz = sponge_index(r0 + i, g.nzp, g.nbc);
             smem[kap_off + i] = (i < nrows && kz >= 0) ? kap_b[kz] : 0.0f;
@@ -194,76 +252,102 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_adj_cluster(ClusterAdjAr
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (th.src_lr >= 0 && th.x + j < g.nxp && th.x + j == xs) src_lane = j;
-        float4 Ga[RMAX], Gk[RMAX];
+        float4 Ga[RMAX], Gk[RMAX];  // in marching order
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) { Ga[r] = zero4; Gk[r] = zero4; }
         float gb = 0.0f;
         fence_proxy_async();
         __syncthreads();
-        cluster_sync_all();
-        if (tid == 0 && a.nt >= 2) load_level(shot, a.nt - 2);
+        cluster_sync_all();  // shot boundary
+        if (tid == 0) {      // history prefetch runs two levels ahead
+            if (a.nt >= 2) load_level(shot, a.nt - 2);
+            if (a.nt >= 3) load_level(shot, a.nt - 3);
+        }
 
         // one reverse level: u_{t+1} in buffer `cur`, u_{t+2} in `prv`, u_t overwrites u_{t+2}
         auto level = [&](const int t, const int cur, const int prv) {
+            const int k = a.nt - 1 - t;  // reverse level counter, 0-based
+            const int cbuf = cur == 0 ? 0 : 1, pbuf = 1 - cbuf;
+            uint64_t *bar_top = bars + 2 * cbuf, *bar_bot = bars + 2 * cbuf + 1;
+            const bool sends = t > 0;  // u_0 has no consumer
+            if (k >= 1) {
+                const uint32_t parity = (uint32_t)((shot_iter * (cbuf ? uses1 : uses0) + (k - 1) / 2) & 1);
+                if (tid == 0) {
+                    mbar_expect_tx(bar_top, halo_bytes);
+                    mbar_expect_tx(bar_bot, halo_bytes);
+                }
+                if (warp_active) {
+                    if (rd_top) mbar_wait(bar_top, parity);
+                    if (rd_bot) mbar_wait(bar_bot, parity);
+                }
+            }
             const int p0 = prv + 2 * pitch + th.x;
             if (warp_active) {
-                adj_sweep<RMAX, PITCH>(smem, cur, prv, al_off, kap_off, pitch, th, kapx);
+                const uint64_t *push_bar = bars + 2 * pbuf + hp.bar;
+                if (rev) adj_sweep<RMAX, PITCH, -1>(smem, cur, prv, kap_off, pitch, l0, th, alpha_row0, kapx, hp, push_bar, hp.early && sends);
+                else adj_sweep<RMAX, PITCH, 1>(smem, cur, prv, kap_off, pitch, l0, th, alpha_row0, kapx, hp, push_bar, hp.early && sends);
                 if (th.rec_lr >= 0 && t % a.st == 0) {  // u_t[rec] += alpha * g_t  (adjoint of the gather, :83)
                     const float *gt = a.cot + ((size_t)shot * g.nt_out + t / a.st) * g.nrec;
                     float4 v = ld4(smem + p0 + th.rec_lr * pitch);
-                    const float4 alv = ld4(smem + al_off + th.rec_lr * pitch + th.x);
+                    const float4 alv = __ldg(reinterpret_cast<const float4 *>(alpha_row0 + (size_t)th.rec_lr * pitch + th.x));
                     float add[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        for (int k = a.rec_ptr[xc[j]]; k < a.rec_ptr[xc[j] + 1]; ++k) add[j] += gt[a.rec_idx[k]];
+                        for (int q = s_rec_ptr[xc[j]]; q < s_rec_ptr[xc[j] + 1]; ++q) add[j] += gt[s_rec_idx[q]];
                     v.x += alv.x * add[0]; v.y += alv.y * add[1]; v.z += alv.z * add[2]; v.w += alv.w * add[3];
                     st4(smem + p0 + th.rec_lr * pitch, v);
                 }
                 if (src_lane >= 0) {  // adjoint of the source injection (:81)
                     const float4 v = ld4(smem + p0 + th.src_lr * pitch);
-                    gb += (src_lane == 0 ? v.x : src_lane == 1 ? v.y : src_lane == 2 ? v.z : v.w) * a.wavelet[t];
+                    gb += (src_lane == 0 ? v.x : src_lane == 1 ? v.y : src_lane == 2 ? v.z : v.w) * (wav_in_smem ? s_wav[t] : a.wavelet[t]);
                 }
-                if (th.la < 2)
-                    for (int h = th.la; h < 2 && h < th.lb; ++h)
-                        st_cluster_v4(smem + prv + (2 + nrows_up + h) * pitch + th.x, (uint32_t)up, ld4(smem + p0 + h * pitch));
-                if (th.lb > nrows - 2)
-                    for (int h = (th.la > nrows - 2 ? th.la : nrows - 2); h < th.lb; ++h)
-                        st_cluster_v4(smem + prv + (h - (nrows - 2)) * pitch + th.x, (uint32_t)dn, ld4(smem + p0 + h * pitch));
+                if (late != 0 && sends) {
+                    for (int h = 0; h < 2; ++h) {
+                        if (late & (1 << h))
+                            st_async_v4(smem + prv + (2 + nrows_up + h) * pitch + th.x, bars + 2 * pbuf + 1, (uint32_t)up,
+                                        ld4(smem + p0 + h * pitch));
+                        if (late & (4 << h))
+                            st_async_v4(smem + prv + h * pitch + th.x, bars + 2 * pbuf, (uint32_t)dn,
+                                        ld4(smem + p0 + (nrows - 2 + h) * pitch));
+                    }
+                }
             }
             if (t >= 1) {
-                mbar_wait(mbar, phase);  // forward level t-1 has landed in the p slab
-                phase ^= 1u;
-                if (warp_active) imaging_sweep<RMAX, PITCH>(smem, cur, prv, pbuf, pitch, th, Ga, Gk);
+                // forward level t-1 sits in history slab ((t-1) & 1); its load was issued two levels ago
+                const int hs = (t - 1) & 1;
+                const int nth = (a.nt - 2 - (t - 1)) / 2;  // how many loads into this slab preceded it in this shot
+                const uint32_t hpar = (uint32_t)((shot_iter * (hs ? loads1 : loads0) + nth) & 1);
+                mbar_wait(bars + 4 + hs, hpar);
+                if (warp_active) {
+                    if (rev) imaging_sweep<RMAX, PITCH, -1>(smem, cur, prv, pslab0 + hs * slab, pitch, l0, th, Ga, Gk);
+                    else imaging_sweep<RMAX, PITCH, 1>(smem, cur, prv, pslab0 + hs * slab, pitch, l0, th, Ga, Gk);
+                }
             }
-            cluster_sync_all();
-            if (tid == 0 && t >= 2) load_level(shot, t - 2);
+            __syncthreads();  // level t complete CTA-wide; history slab ((t-1)&1) is free again
+            if (tid == 0 && t >= 3) load_level(shot, t - 3);
         };
-        int t = a.nt - 1;
-        for (; t >= 1; t -= 2) {
-            level(t, 0, slab);
-            level(t - 1, slab, 0);
-        }
-        if (t == 0) level(0, 0, slab);
+        for (int t = a.nt - 1, cur = 0; t >= 0; --t, cur = slab - cur) level(t, cur, slab - cur);
 
         // per-shot imaging planes (divided by alpha, see header) -- summed over shots by the epilogue kernels
         if (active) {
-            float *ga_out = a.Ga + (size_t)shot * g.level + (size_t)(r0 + th.la) * pitch + th.x;
-            float *gk_out = a.Gk + (size_t)shot * g.level + (size_t)(r0 + th.la) * pitch + th.x;
 #pragma unroll
             for (int r = 0; r < RMAX; ++r) {
-                if (th.la + r < th.lb) {
-                    const float4 alv = ld4(smem + al_off + (th.la + r) * pitch + th.x);
-                    st4(ga_out + r * pitch, make_float4(Ga[r].x / alv.x, Ga[r].y / alv.y, Ga[r].z / alv.z, Ga[r].w / alv.w));
-                    st4(gk_out + r * pitch, make_float4(Gk[r].x / alv.x, Gk[r].y / alv.y, Gk[r].z / alv.z, Gk[r].w / alv.w));
+                const int lr = rev ? l0 - r : l0 + r;
+                if (lr >= th.la && lr < th.lb) {
+                    const size_t off = (size_t)(r0 + lr) * pitch + th.x;
+                    const float4 alv = __ldg(reinterpret_cast<const float4 *>(a.alpha + (size_t)b * g.level + off));
+                    st4(a.Ga + (size_t)shot * g.level + off, make_float4(Ga[r].x / alv.x, Ga[r].y / alv.y, Ga[r].z / alv.z, Ga[r].w / alv.w));
+                    st4(a.Gk + (size_t)shot * g.level + off, make_float4(Gk[r].x / alv.x, Gk[r].y / alv.y, Gk[r].z / alv.z, Gk[r].w / alv.w));
                 }
             }
             if (src_lane >= 0) {
-                const float4 alv = ld4(smem + al_off + th.src_lr * pitch + th.x);
+                const float4 alv = __ldg(reinterpret_cast<const float4 *>(alpha_row0 + (size_t)th.src_lr * pitch + th.x));
                 a.Gb[shot] = gb / (src_lane == 0 ? alv.x : src_lane == 1 ? alv.y : src_lane == 2 ? alv.z : alv.w);
             }
         }
         __syncthreads();
     }
+    cluster_sync_all();  // no CTA exits while a neighbour may still address its shared memory
 }
 
 template <int RMAX>
@@ -279,8 +363,10 @@ bool adj_config_rmax(const Plan &p, int max_smem, ClusterConfig *cfg)
         const int ngroups = (maxrows + RMAX - 1) / RMAX;
         if (ngroups > groups_max) continue;
         const int slabrows = ngroups * RMAX;
-        const size_t smem = ((size_t)3 * (slabrows + 4) * g.pitch + (size_t)slabrows * g.pitch + slabrows + 16) * sizeof(float);
+        size_t smem = ((size_t)4 * (slabrows + 4) * g.pitch + slabrows + 24 + g.nxp + 1 + g.nrec) * sizeof(float);
         if (smem > (size_t)max_smem) continue;
+        cfg->wav_smem = smem + (size_t)p.nt * sizeof(float) <= (size_t)max_smem;
+        if (cfg->wav_smem) smem += (size_t)p.nt * sizeof(float);
         cfg->C = C; cfg->maxrows = maxrows; cfg->ngroups = ngroups; cfg->slabrows = slabrows; cfg->smem = smem; cfg->rmax = RMAX;
         return true;
     }
@@ -293,7 +379,7 @@ cudaError_t launch_adj_cluster_t(const Plan &p, const ClusterConfig &cc, Cluster
     auto kernel = k_adj_cluster<RMAX, PITCH>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
     if (e != cudaSuccess) return e;
-    a.slabrows = cc.slabrows; a.ngroups = cc.ngroups;
+    a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

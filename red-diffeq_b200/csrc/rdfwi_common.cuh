@@ -76,7 +76,7 @@ struct ClusterFwdArgs {
     float *seis;            // (B*ns, nt_out, nrec)
     float *hist;            // [shot][t][z][x], t = 0..nt-2, or nullptr
     int nshots, nt, st;
-    int slabrows, ngroups;  // filled by launch_fwd_cluster from the ClusterConfig
+    int slabrows, ngroups, wav_smem;  // filled by launch_fwd_cluster from the ClusterConfig
 };
 
 // Cluster-resident reverse-time loop (kernels_cluster_adj.cu).
@@ -93,7 +93,7 @@ struct ClusterAdjArgs {
     float *Gk;             // (B*ns, nzp, pitch)
     float *Gb;             // (B*ns)
     int nshots, nt, st;
-    int slabrows, ngroups;  // filled by the launcher from the ClusterConfig
+    int slabrows, ngroups, wav_smem;  // filled by the launcher from the ClusterConfig
 };
 
 struct ClusterConfig {
@@ -103,6 +103,7 @@ struct ClusterConfig {
     int slabrows = 0; // ngroups * kClusterRowsMax >= maxrows (rows allocated per buffer, halos excluded)
     size_t smem = 0;  // dynamic shared memory per CTA
     int rmax = 0;     // rows per thread (template instantiation) of the adjoint kernel
+    bool wav_smem = false;  // the wavelet is staged in shared memory
 };
 
 // Pointers of one step launch (forward).
