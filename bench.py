@@ -32,16 +32,33 @@ ALGO_BYTES_PAIR = ALGO_BYTES_FWD + ALGO_BYTES_ADJ
 
 WORKLOADS = {
     # name: (pde ctx factory, nz, nx, models per GPU)
-    "openfwi_b64": ("openfwi", 70, 70, 64),
-    "openfwi_b1": ("openfwi", 70, 70, 1),
-    "marmousi_b1": ("marmousi", 70, 190, 1),
+    "openfwi_b64": ("openfwi", 70, 70, 64),       # BASELINE.json configs[1]: the headline (weak scaling: 64 models per GPU)
+    "openfwi_b1": ("openfwi", 70, 70, 1),         # configs[0]
+    "marmousi_b1": ("marmousi", 70, 190, 1),      # configs[2] shape, reference shot count (5)
     "marmousi_b16": ("marmousi", 70, 190, 16),
+    # configs[2]: ONE Marmousi-shaped model, 40 shots (the reference's 5 do not divide over 8 GPUs)
+    # sharded over the ranks by ShardedFWIForward: strong scaling, one gradient all-reduce per step
+    "marmousi_sharded": ("marmousi40", 70, 190, 1),
+}
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the `ncu --set full`
+# capture of the same workload committed under profiles/ (None = not captured for this workload)
+NCU_TRAFFIC_BYTES = {
+    # profiles/ncu_adj_cluster_r1_full_b64.txt: 123.85 GB read + 0.28 GB written by the one k_adj_cluster launch
+    ("openfwi_b64", "adjoint"): 124.13e9,
+    # profiles/ncu_fwd_cluster_r1_v5.txt (8 models, 200 levels: 3.03 GB written) scaled to 64 models x 999 stored levels
+    ("openfwi_b64", "forward"): 121.8e9,
 }
 
 
 def make_ctx(kind):
     from red_diffeq_b200.utils import synthetic
-    return dict(synthetic.PDE_OPENFWI if kind == "openfwi" else synthetic.PDE_MARMOUSI)
+    if kind == "openfwi":
+        return dict(synthetic.PDE_OPENFWI)
+    ctx = dict(synthetic.PDE_MARMOUSI)
+    if kind == "marmousi40":
+        ctx["ns"] = 40
+    return ctx
 
 
 def measured_peak_gbs():
@@ -171,7 +188,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize
+    from red_diffeq_b200 import FWIForward, ShardedFWIForward, s_normalize_none, v_denormalize
     from red_diffeq_b200.utils import synthetic
 
     if not torch.cuda.is_available():
@@ -187,19 +204,31 @@ def main():
     ctx = make_ctx(kind)
     if args.nt:
         ctx["nt"] = args.nt
-    op = FWIForward(dict(ctx), dev, normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    sharded = args.workload == "marmousi_sharded"
+    ns, nt, nbc = ctx["ns"], ctx["nt"], ctx["nbc"]
+    nzp, nxp = nz + 2 * nbc, nx + 2 * nbc
+    if sharded:
+        # strong scaling: the same 1 x 40 shots whatever the rank count; every rank models its shots
+        wrapper = ShardedFWIForward(dict(ctx), dev, mode="shots", normalize=True, v_denorm_func=v_denormalize,
+                                    s_norm_func=s_normalize_none)
+        _, _, my_shots = wrapper.partition(B)
+        op = wrapper._operator(my_shots)
+        ns_local = len(my_shots)
+    else:
+        wrapper = None
+        op = FWIForward(dict(ctx), dev, normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+        ns_local = ns
     for kv in args.opt:
         k, v = kv.split("=")
         op.set_option(k, int(v))
-    ns, nt, nbc = ctx["ns"], ctx["nt"], ctx["nbc"]
-    nzp, nxp = nz + 2 * nbc, nx + 2 * nbc
-    pairs_rank = B * ns * nzp * nxp * nt
-    cells_level = B * ns * nzp * nxp
+    pairs_rank = B * ns_local * nzp * nxp * nt
+    cells_level = B * ns_local * nzp * nxp
 
     # synthetic inputs (seed 8888 + rank): models, and "observed" data = a fixed random record so that the
     # L1 misfit of the e2e path has a non-trivial cotangent
-    vn_host = torch.from_numpy(synthetic.velocity_models(B, nz, nx, seed=synthetic.SEED + rank)).pin_memory()
-    y_host = torch.from_numpy(synthetic.cotangent((B, ns, nt, ctx["ng"]), seed=17 + rank)).pin_memory()
+    model_seed = synthetic.SEED if sharded else synthetic.SEED + rank   # sharded: the model is replicated
+    vn_host = torch.from_numpy(synthetic.velocity_models(B, nz, nx, seed=model_seed)).pin_memory()
+    y_host = torch.from_numpy(synthetic.cotangent((B, ns_local, nt, ctx["ng"]), seed=17 + rank)).pin_memory()
     grad_host = torch.empty((B, 1, nz, nx), dtype=torch.float32).pin_memory()
     loss_host = torch.empty((B,), dtype=torch.float32).pin_memory()
     v_dev = vn_host.to(dev)
@@ -210,11 +239,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    fwd = wrapper if sharded else op   # the sharded wrapper adds the gradient all-reduce to backward()
+
     def step_resident():
         v = v_dev.detach().requires_grad_(True)
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        seis = op(v)
+        seis = fwd(v)
         launches_f = op.last_launches
         e1.record()
         seis.backward(cot_dev)
@@ -224,7 +255,7 @@ def main():
     def step_e2e():
         v = vn_host.to(dev, non_blocking=True).requires_grad_(True)
         y = y_host.to(dev, non_blocking=True)
-        seis = op(v)
+        seis = fwd(v)
         loss = (seis - y).abs().mean(dim=(1, 2, 3))          # the reference's L1 data misfit (core/losses.py:27-41)
         loss.sum().backward()
         grad_host.copy_(v.grad, non_blocking=True)
@@ -266,13 +297,23 @@ def main():
         t = torch.tensor([elapsed_ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, e2e_ms = t.tolist()
+        tot = torch.tensor([float(pairs_rank)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        pairs_total = tot.item()
+    else:
+        pairs_total = float(pairs_rank)
 
     if rank == 0:
         ms_per_step = elapsed_ms / args.steps
-        value = pairs_rank * world / (ms_per_step * 1e-3)
-        e2e_value = pairs_rank * world / (e2e_ms / args.steps * 1e-3)
+        value = pairs_total / (ms_per_step * 1e-3)
+        e2e_value = pairs_total / (e2e_ms / args.steps * 1e-3)
         peak, peak_src = measured_peak_gbs()
-        # dominant kernel = the adjoint step (k_adj_step): all shots of a chunk, one time level per launch
+        # dominant kernel = the adjoint time loop: k_adj_cluster (cluster-resident engine: ONE launch runs all
+        # levels of all shots) or k_adj_step (per-level engine: one launch per level per chunk of models)
+        plan = op._plan_for(nz, nx, dev)
+        eng = op.options.get("engine", 0)
+        adj_cluster = eng != 1 and plan.get("adj_cluster_size_used") > 0
+        fwd_cluster = eng != 1 and plan.get("cluster_size_used") > 0
         step_launches_b = max(launches_b - 7, 1)      # minus prologue (3) + epilogue (4) launches
         adj_launch_s = adj_ms * 1e-3 / step_launches_b
         bytes_per_launch = ALGO_BYTES_ADJ * cells_level * nt / step_launches_b
@@ -282,21 +323,28 @@ def main():
         line = {
             "metric": "FD cell-updates/s (fwd+adjoint)", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "models_per_gpu": B, "shots_per_model": ns, "nt": nt,
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "models_per_gpu": B, "shots_per_model": ns,
+                       "shots_on_rank0": ns_local, "nt": nt,
                        "padded_grid": [nzp, nxp], "pairs_per_step_per_gpu": pairs_rank,
                        "l2_policy": "working set (wavefield history %.1f GB) far exceeds the 126 MB L2; no flush needed"
                                     % (op._plan_for(nz, nx, dev).history_bytes(B) / 1e9),
+                       "engine": {"forward": "cluster-resident (C=%d)" % plan.get("cluster_size_used") if fwd_cluster else "per-level",
+                                  "adjoint": "cluster-resident (C=%d)" % plan.get("adj_cluster_size_used") if adj_cluster else "per-level"},
                        "options": dict(op.options)},
             "e2e": {"value": e2e_value, "unit": "pairs/s",
                     "h2d_bytes_per_step": int(vn_host.numel() * 4 + y_host.numel() * 4),
                     "d2h_bytes_per_step": int(grad_host.numel() * 4 + loss_host.numel() * 4)},
             "gpu_launches": int((launches_f + launches_b) * args.steps),
-            "roofline": {"bound": "hbm", "kernel": "k_adj_step", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k_adj_cluster" if adj_cluster else "k_adj_step", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "adjoint")), "peak_source": peak_src,
+                         "algorithmic_bytes_per_cell_update": ALGO_BYTES_ADJ,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": adj_launch_s * 1e6,
                          "launches_per_step": step_launches_b,
-                         "forward": {"kernel": "k_fwd_step", "achieved": fwd_achieved, "frac": fwd_achieved / peak,
+                         "forward": {"kernel": "k_fwd_cluster" if fwd_cluster else "k_fwd_step", "achieved": fwd_achieved,
+                                     "frac": fwd_achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "forward")),
+                                     "algorithmic_bytes_per_cell_update": ALGO_BYTES_FWD,
                                      "avg_launch_us": fwd_ms * 1e3 / step_launches_f, "launches_per_step": step_launches_f},
                          "pair_frac": (ALGO_BYTES_PAIR * pairs_rank / ((fwd_ms + adj_ms) * 1e-3) / 1e9) / peak},
             "phase_ms": {"forward": fwd_ms, "adjoint": adj_ms},

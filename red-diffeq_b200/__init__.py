@@ -6,7 +6,8 @@ Import it as ``red_diffeq_b200`` (the shim red_diffeq_b200.py at the repo root m
 name onto this directory, whose name has a hyphen).
 """
 from .solvers.pde import FWIForward
+from .solvers.sharding import ShardedFWIForward
 from .utils.data_trans import s_normalize_none, v_denormalize, v_normalize
 
 __version__ = "0.1.0"
-__all__ = ["FWIForward", "v_normalize", "v_denormalize", "s_normalize_none"]
+__all__ = ["FWIForward", "ShardedFWIForward", "v_normalize", "v_denormalize", "s_normalize_none"]

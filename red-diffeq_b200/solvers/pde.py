@@ -114,8 +114,10 @@ class FWIForward(nn.Module):
     """
 
     def __init__(self, ctx, device, sample_temporal=1, sample_spatial=1.0, normalize=True, v_denorm_func=None,
-                 s_norm_func=None):
+                 s_norm_func=None, shot_subset=None):
         super().__init__()
+        # shot_subset (extension, used by ShardedFWIForward): indices of the shots this instance models
+        self._shot_subset = None if shot_subset is None else np.asarray(shot_subset, dtype=np.int64)
         self.device = device
         self.normalize = normalize
         if normalize:
@@ -148,6 +150,8 @@ class FWIForward(nn.Module):
                 c = self.ctx
                 wavelet = _survey.ricker(c["f"], c["dt"], c["nt"])
                 isx, isz, igx, igz = _survey.grid_indices(c["sx"], c["sz"], c["gx"], c["gz"], c["dx"], c["nbc"])
+                if self._shot_subset is not None:
+                    isx = isx[self._shot_subset]
                 nzp, nxp = nz + 2 * c["nbc"], nx + 2 * c["nbc"]
                 isx = _survey.wrap_indices(isx, nxp, "source column")
                 igx = _survey.wrap_indices(igx, nxp, "receiver column")

@@ -1,0 +1,87 @@
+"""CPU, 2 processes over gloo: the shot/model partitioner + single gradient all-reduce reproduce the
+single-process gradient.  The per-rank operator is a stand-in built on the CPU oracle (the CUDA operator
+needs a GPU); what is under test is the host logic of ShardedFWIForward."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+from conftest import ROOT  # noqa: E402
+
+CTX = dict(n_grid=16, nt=130, dx=10.0, dt=0.001, nbc=8, f=25.0, sz=10, gz=10, ng=16, ns=4)
+NZ, NX = 12, 16
+
+
+class _OracleOp(torch.nn.Module):
+    """FWIForward-shaped stand-in: forward + adjoint through the CPU oracle (physical velocities in, no normalisation)."""
+
+    def __init__(self, ctx, device, shot_subset=None):
+        super().__init__()
+        from oracle import fwi_oracle
+        ctx = dict(ctx)
+        if shot_subset is not None:  # sources of this shard, in grid units like a user-supplied ctx['sx']
+            all_sx = np.linspace(0, ctx["n_grid"] - 1, num=ctx["ns"])
+            ctx["sx"] = list(all_sx[list(shot_subset)])
+        self.oracle, self.survey = fwi_oracle, fwi_oracle.Survey(ctx, NZ, NX)
+
+    def forward(self, v):
+        oracle, survey = self.oracle, self.survey
+
+        class Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, v):
+                ctx.save_for_backward(v)
+                return torch.from_numpy(oracle.forward(survey, v.detach().numpy()))
+
+            @staticmethod
+            def backward(ctx, g):
+                (v,) = ctx.saved_tensors
+                _, grad = oracle.gradient(survey, v.numpy(), g.contiguous().numpy())
+                return torch.from_numpy(grad)
+
+        return Fn.apply(v)
+
+
+def _worker(rank, world, port, mode, B, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from red_diffeq_b200.solvers.sharding import ShardedFWIForward
+    rng = np.random.default_rng(5)
+    v_np = (1500 + 3000 * rng.random((B, 1, NZ, NX))).astype(np.float32)
+    y_np = rng.standard_normal((B, CTX["ns"], CTX["nt"], CTX["ng"])).astype(np.float32)
+    op = ShardedFWIForward(dict(CTX), "cpu", mode=mode, operator_factory=lambda ctx, dev, shot_subset=None: _OracleOp(ctx, dev, shot_subset))
+    v = torch.tensor(v_np, requires_grad=True)
+    seis = op(v)
+    y = op.local_slice(torch.tensor(y_np))
+    loss = ((seis - y) ** 2).sum() / y_np.size        # global normaliser
+    loss.backward()
+    tot = loss.detach().clone()
+    dist.all_reduce(tot)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), grad=v.grad.numpy(), loss=tot.numpy(), shape=np.array(seis.shape))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,B", [("models", 2), ("shots", 1), ("auto", 3)])
+def test_sharded_gradient_equals_single_process(tmp_path, mode, B, oracle):
+    port = 29500 + (os.getpid() + hash(mode)) % 2000
+    mp.spawn(_worker, args=(2, port, mode, B, str(tmp_path)), nprocs=2, join=True)
+    rng = np.random.default_rng(5)
+    v_np = (1500 + 3000 * rng.random((B, 1, NZ, NX))).astype(np.float32)
+    y_np = rng.standard_normal((B, CTX["ns"], CTX["nt"], CTX["ng"])).astype(np.float32)
+    survey = oracle.Survey(dict(CTX), NZ, NX)
+    seis = oracle.forward(survey, v_np)
+    cot = (2.0 * (seis - y_np) / y_np.size).astype(np.float32)
+    _, grad = oracle.gradient(survey, v_np, cot)
+    loss = ((seis - y_np) ** 2).sum() / y_np.size
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert np.array_equal(r0["grad"], r1["grad"])                       # every rank holds the full gradient
+    assert np.allclose(r0["loss"], loss, rtol=1e-5)
+    rel = np.linalg.norm(r0["grad"] - grad) / np.linalg.norm(grad)
+    assert rel < 1e-5, rel
+    assert int(r0["shape"][0]) * int(r0["shape"][1]) + int(r1["shape"][0]) * int(r1["shape"][1]) == B * CTX["ns"]
