@@ -356,7 +356,8 @@ bool adj_config_rmax(const Plan &p, int max_smem, ClusterConfig *cfg)
     const Grid &g = p.g;
     const int groups_max = kClusterThreads / g.q4;
     if (groups_max < 1) return false;
-    for (int C = 1; C <= 8; ++C) {
+    for (int C = 1; C <= 16; ++C) {
+        if (C > 8 && C != 16) continue;  // 1..8 are portable cluster sizes, 16 needs the non-portable opt-in
         if (p.adj_cluster_size > 0 && C != p.adj_cluster_size) continue;
         if (g.nzp / C < 2) break;
         const int maxrows = (g.nzp + C - 1) / C;
@@ -380,6 +381,10 @@ cudaError_t launch_adj_cluster_t(const Plan &p, const ClusterConfig &cc, Cluster
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
     if (e != cudaSuccess) return e;
     a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
+    if (cc.C > 8) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -412,10 +417,14 @@ bool adj_cluster_config(const Plan &p, ClusterConfig *cfg)
     ClusterConfig best;
     bool found = false;
     ClusterConfig c;
-    // prefer the configuration with the smallest cluster (most work per barrier), ties -> more threads
-    if (adj_config_rmax<7>(p, max_smem, &c)) { best = c; found = true; }
-    if (adj_config_rmax<5>(p, max_smem, &c) && (!found || c.C < best.C)) { best = c; found = true; }
-    if (adj_config_rmax<10>(p, max_smem, &c) && (!found || c.C < best.C)) { best = c; found = true; }
+    // smallest cluster first (most work per synchronisation), then the most active threads
+    auto consider = [&](bool ok) {
+        if (ok && (!found || c.C < best.C || (c.C == best.C && c.ngroups > best.ngroups))) { best = c; found = true; }
+    };
+    consider(adj_config_rmax<7>(p, max_smem, &c));
+    consider(adj_config_rmax<5>(p, max_smem, &c));
+    consider(adj_config_rmax<10>(p, max_smem, &c));
+    consider(adj_config_rmax<4>(p, max_smem, &c));
     if (found) *cfg = best;
     return found;
 }
@@ -429,6 +438,7 @@ cudaError_t launch_adj_cluster(const Plan &p, const ClusterConfig &cc, ClusterAd
         default: return launch_adj_cluster_t<R, 0>(p, cc, a, st);                    \
     }
     switch (cc.rmax) {
+        case 4: RD_DISPATCH(4)
         case 5: RD_DISPATCH(5)
         case 7: RD_DISPATCH(7)
         default: RD_DISPATCH(10)

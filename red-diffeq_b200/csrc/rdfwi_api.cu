@@ -236,7 +236,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "use_graph") { p->use_graph = value != 0; }
     else if (k == "engine") { if (value < 0 || value > 2) goto bad; p->engine = (int)value; }
     else if (k == "cluster_size") { if (value < 0 || value > 8) goto bad; p->cluster_size = (int)value; }
-    else if (k == "adj_cluster_size") { if (value < 0 || value > 8) goto bad; p->adj_cluster_size = (int)value; }
+    else if (k == "adj_cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->adj_cluster_size = (int)value; }
     else { set_error("unknown option " + k); return RDFWI_EINVAL; }
     return RDFWI_OK;
 bad:
