@@ -64,8 +64,12 @@ int rdfwi_plan_destroy(rdfwi_plan plan);
 
 /* Tunables (all optional).  Keys:
  *   "chunk_models"   models advanced together through the time loop (0 = auto: sized for L2)
- *   "rows_per_thread" 1, 2 or 4: z-rows marched per thread in the forward step kernel
- *   "use_graph"      1 = replay the time loop as a CUDA graph (default), 0 = plain launches      */
+ *   "rows_per_thread" / "adj_rows_per_thread"  z-rows marched per thread in the per-level step kernels
+ *   "engine"         0 = by problem size (default), 1 = per-level kernels, 2 = cluster-resident time loop
+ *   "cluster_size" / "adj_cluster_size"  CTAs per cluster of the cluster-resident kernels (0 = smallest that fits)
+ *   "history_segment" 0 = keep every level, K >= 3 = checkpoint pairs every K levels (must be set BEFORE the
+ *                    workspace / history sizes are queried; forward/backward's `segment` must equal it)
+ * rdfwi_plan_get additionally answers "pitch", "nzp", "nxp", "nt_out", "cluster_size_used", "adj_cluster_size_used". */
 int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value);
 int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *value_out);
 
@@ -77,7 +81,9 @@ size_t rdfwi_workspace_bytes(rdfwi_plan plan, int32_t B);
 
 /* Bytes of wavefield history rdfwi_forward must be given so that rdfwi_backward can run.
  *   segment == 0 : every level is kept (B*ns*(nt-1) levels)
- *   segment == K : checkpoint pairs every K levels, the backward pass recomputes K levels at a time */
+ *   segment == K : the pair (p_{jK-2}, p_{jK-1}) in front of every segment j >= 1 of K levels is kept; the backward
+ *                  pass recomputes one segment at a time into the workspace (one extra forward, memory / (K/2)).
+ *                  May be 0 bytes (single segment): a NULL history is then accepted by rdfwi_backward. */
 size_t rdfwi_history_bytes(rdfwi_plan plan, int32_t B, int32_t segment);
 
 /*

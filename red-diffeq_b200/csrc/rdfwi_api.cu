@@ -71,6 +71,7 @@ struct Workspace {
     size_t chunk_level = 0;  // floats of one level of a full chunk
     int nb = 0;
     int g_planes = 1;
+    float *seg_hist = nullptr;
 };
 
 Workspace carve(const Plan &p, int B, void *base)
@@ -95,12 +96,15 @@ Workspace carve(const Plan &p, int B, void *base)
     w.fields = (float *)take(3 * w.chunk_level * 4);
     w.zero = (float *)take(w.chunk_level * 4);
     ClusterConfig acc;
-    w.g_planes = (p.engine != 1 && adj_cluster_config(p, &acc)) ? g.ns : 1;  // per-shot planes for the cluster adjoint
+    // per-shot imaging planes for the cluster adjoint; checkpointed histories run on the per-level engine
+    w.g_planes = (p.engine != 1 && p.history_segment == 0 && adj_cluster_config(p, &acc)) ? g.ns : 1;
     w.Ga = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gk = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gb = (float *)take((size_t)B * g.ns * 4);
     w.fold_tmp = (float *)take((size_t)B * g.nz * g.nxp * 4);
     w.vel_part = (double *)take((size_t)B * kMinBlocks * 8);
+    // checkpoint mode: the levels of one segment of one chunk, recomputed during the backward pass
+    w.seg_hist = p.history_segment > 0 ? (float *)take(w.chunk_level * (size_t)(p.history_segment - 1) * 4) : nullptr;
     w.bytes = off;
     return w;
 }
@@ -120,10 +124,23 @@ int check_common(rdfwi_plan plan, const void *v, int B, const void *ws, size_t w
     return RDFWI_OK;
 }
 
+int num_segments(const Plan &p, int segment) { return (p.nt + segment - 1) / segment; }
+
 size_t history_floats(const Plan &p, int B, int segment)
 {
-    if (segment != 0) return 0;
+    if (segment > 0)  // the pair (p_{jK-2}, p_{jK-1}) in front of every segment j >= 1
+        return (size_t)B * p.g.ns * (size_t)std::max(num_segments(p, segment) - 1, 0) * 2 * p.g.level;
     return (size_t)B * p.g.ns * (size_t)std::max(p.nt - 1, 0) * p.g.level;
+}
+
+int check_segment(const Plan &p, int segment)
+{
+    if (segment != p.history_segment) {
+        set_error("segment argument (" + std::to_string(segment) + ") differs from the plan's history_segment option (" +
+                  std::to_string(p.history_segment) + "): set it with rdfwi_plan_set before sizing the workspace");
+        return RDFWI_EINVAL;
+    }
+    return RDFWI_OK;
 }
 
 }  // namespace
@@ -235,6 +252,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "adj_rows_per_thread") { if (value != 1 && value != 2) goto bad; p->adj_rows_per_thread = (int)value; }
     else if (k == "use_graph") { p->use_graph = value != 0; }
     else if (k == "engine") { if (value < 0 || value > 2) goto bad; p->engine = (int)value; }
+    else if (k == "history_segment") { if (value < 0 || value == 1 || value == 2) goto bad; p->history_segment = (int)value; }
     else if (k == "cluster_size") { if (value < 0 || value > 8) goto bad; p->cluster_size = (int)value; }
     else if (k == "adj_cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->adj_cluster_size = (int)value; }
     else { set_error("unknown option " + k); return RDFWI_EINVAL; }
@@ -254,6 +272,7 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
     else if (k == "adj_rows_per_thread") *out = p->adj_rows_per_thread;
     else if (k == "use_graph") *out = p->use_graph;
     else if (k == "engine") *out = p->engine;
+    else if (k == "history_segment") *out = p->history_segment;
     else if (k == "cluster_size") *out = p->cluster_size;
     else if (k == "cluster_size_used") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cc.C : 0; }
     else if (k == "adj_cluster_size_used") { ClusterConfig cc; *out = adj_cluster_config(*p, &cc) ? cc.C : 0; }
@@ -302,7 +321,7 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
     const Plan &p = *reinterpret_cast<Plan *>(plan);
     const Grid &g = p.g;
     if (history) {
-        if (segment != 0) { set_error("checkpointed history (segment > 0) is not available in this build"); return RDFWI_EINVAL; }
+        if ((rc = check_segment(p, segment)) != RDFWI_OK) return rc;
         if (history_bytes < history_floats(p, B, segment) * sizeof(float)) { set_error("history buffer too small"); return RDFWI_ESIZE; }
     }
     DeviceGuard guard(p.device);
@@ -312,8 +331,9 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
     RD_CUDA(launch_coefficients(p, v, B, w.alpha, w.kap, w.velmin, w.argmin, w.beta_src, w.minpart, st));
     float *hist = static_cast<float *>(history);
     const int nt = p.nt;
+    const bool ckpt = hist && segment > 0;  // checkpointed history: per-level engine
     ClusterConfig cc;
-    if (p.engine != 1 && cluster_config(p, &cc)) {
+    if (p.engine != 1 && !ckpt && cluster_config(p, &cc)) {
         // cluster-resident time loop: one launch for all shots and all levels
         ClusterFwdArgs a{};
         a.alpha = w.alpha; a.kap = w.kap; a.beta_src = w.beta_src;
@@ -323,18 +343,32 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
         RD_CUDA(launch_fwd_cluster(p, cc, a, st));
         return RDFWI_OK;
     }
-    if (p.engine == 2) { set_error("engine=2 (cluster-resident) requested but the grid does not fit a cluster"); return RDFWI_EINVAL; }
+    if (p.engine == 2 && !ckpt) { set_error("engine=2 (cluster-resident) requested but the grid does not fit a cluster"); return RDFWI_EINVAL; }
     if (hist) RD_CUDA(cudaMemsetAsync(w.zero, 0, w.chunk_level * sizeof(float), st));
+    const int K = segment;
+    const size_t ck_stride = ckpt ? (size_t)(num_segments(p, K) - 1) * 2 * g.level : 0;  // shot stride of the checkpoints
 
     for (int b0 = 0; b0 < B; b0 += w.nb) {
         const int nb = std::min(w.nb, B - b0);
         const size_t lvl = (size_t)nb * g.ns * g.level;  // floats per level of this chunk
         const size_t hstride = (size_t)(nt - 1) * g.level;  // shot stride inside the history
         float *hbase = hist ? hist + (size_t)b0 * g.ns * hstride : nullptr;
-        if (!hist) RD_CUDA(cudaMemsetAsync(w.fields, 0, 3 * w.chunk_level * sizeof(float), st));
+        if (!hist || ckpt) RD_CUDA(cudaMemsetAsync(w.fields, 0, 3 * w.chunk_level * sizeof(float), st));
         (void)lvl;
+        float *ck_base = ckpt ? hist + (size_t)b0 * g.ns * ck_stride : nullptr;
         auto level_ptr = [&](int t, unsigned long long *stride) -> float * {
             *stride = g.level;
+            if (ckpt) {
+                // levels jK-2 and jK-1 (j >= 1) live in the checkpoint slots, everything else rotates in scratch
+                if (t >= 0) {
+                    const int j = (t + 2) / K, which = t - (j * K - 2);  // which = 0 or 1 when t is a checkpoint level
+                    if (j >= 1 && j * K < nt && (which == 0 || which == 1)) {
+                        *stride = ck_stride;
+                        return ck_base + ((size_t)(j - 1) * 2 + which) * g.level;
+                    }
+                }
+                return w.fields + (size_t)((t + 3) % 3) * w.chunk_level;
+            }
             if (hist) {
                 if (t < 0) return w.zero;
                 if (t <= nt - 2) { *stride = hstride; return hbase + (size_t)t * g.level; }
@@ -366,10 +400,11 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
 {
     int rc = check_common(plan, v, B, ws, ws_bytes);
     if (rc) return rc;
-    if (!cot || !grad_v || !history) { set_error("null cotangent / gradient / history"); return RDFWI_EINVAL; }
+    if (!cot || !grad_v) { set_error("null cotangent / gradient"); return RDFWI_EINVAL; }
     const Plan &p = *reinterpret_cast<Plan *>(plan);
     const Grid &g = p.g;
-    if (segment != 0) { set_error("checkpointed history (segment > 0) is not available in this build"); return RDFWI_EINVAL; }
+    if ((rc = check_segment(p, segment)) != RDFWI_OK) return rc;
+    if (!history && history_floats(p, B, segment) > 0) { set_error("null history"); return RDFWI_EINVAL; }  // (one segment needs none)
     if (history_bytes < history_floats(p, B, segment) * sizeof(float)) { set_error("history buffer too small"); return RDFWI_ESIZE; }
     DeviceGuard guard(p.device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -378,9 +413,10 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     RD_CUDA(launch_coefficients(p, v, B, w.alpha, w.kap, w.velmin, w.argmin, w.beta_src, w.minpart, st));
     const float *hist = static_cast<const float *>(history);
     const int nt = p.nt;
+    const bool ckpt = segment > 0;
     RD_CUDA(cudaMemsetAsync(w.Gb, 0, (size_t)B * g.ns * sizeof(float), st));
     ClusterConfig cc;
-    if (w.g_planes > 1 && adj_cluster_config(p, &cc)) {
+    if (!ckpt && w.g_planes > 1 && adj_cluster_config(p, &cc)) {
         // cluster-resident reverse-time loop: one launch for all shots and all levels
         ClusterAdjArgs a{};
         a.alpha = w.alpha; a.kap = w.kap; a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
@@ -390,8 +426,11 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
         RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
         return RDFWI_OK;
     }
-    if (p.engine == 2) { set_error("engine=2 (cluster-resident) requested but the adjoint slabs do not fit a cluster"); return RDFWI_EINVAL; }
+    if (p.engine == 2 && !ckpt) { set_error("engine=2 (cluster-resident) requested but the adjoint slabs do not fit a cluster"); return RDFWI_EINVAL; }
     RD_CUDA(cudaMemsetAsync(w.zero, 0, w.chunk_level * sizeof(float), st));
+    const int K = segment;
+    const int nseg = ckpt ? num_segments(p, K) : 1;
+    const size_t ck_stride = ckpt ? (size_t)(nseg - 1) * 2 * g.level : 0;
     RD_CUDA(cudaMemsetAsync(w.Ga, 0, (size_t)B * w.g_planes * g.level * sizeof(float), st));
     RD_CUDA(cudaMemsetAsync(w.Gk, 0, (size_t)B * w.g_planes * g.level * sizeof(float), st));
 
@@ -402,23 +441,52 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
         const float *hbase = hist + (size_t)b0 * g.ns * hstride;
         (void)lvl;
         RD_CUDA(cudaMemsetAsync(w.fields, 0, 3 * w.chunk_level * sizeof(float), st));  // q_{nt} = q_{nt+1} = 0
-        for (int t = nt - 1; t >= 0; --t) {
-            AdjArgs a;
-            a.q1 = w.fields + (size_t)((t + 1) % 3) * w.chunk_level;
-            a.q2 = w.fields + (size_t)((t + 2) % 3) * w.chunk_level;
-            a.out = w.fields + (size_t)(t % 3) * w.chunk_level;
-            a.pm1 = t >= 1 ? hbase + (size_t)(t - 1) * g.level : w.zero;
-            a.ss_pm1 = t >= 1 ? hstride : g.level;
-            a.alpha = w.alpha + (size_t)b0 * g.level;
-            a.kap = w.kap + (size_t)b0 * (g.nbc + 1);
-            a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
-            a.cot = (t % p.st == 0) ? cot + (size_t)b0 * g.ns * g.nt_out * g.nrec : nullptr;
-            a.it_out = t / p.st;
-            a.w_t = p.wavelet[t];
-            a.Ga = w.Ga + (size_t)b0 * g.level;
-            a.Gk = w.Gk + (size_t)b0 * g.level;
-            a.Gb = w.Gb + (size_t)b0 * g.ns;
-            launch_adj_step(p, a, nb, st);
+        const float *ck_base = ckpt ? hist + (size_t)b0 * g.ns * ck_stride : nullptr;
+        // forward level t-1 as seen by adjoint level t: full history, or the segment's recomputed levels / checkpoints
+        auto forward_level = [&](int t, int t0, unsigned long long *stride) -> const float * {
+            *stride = g.level;
+            if (t < 0) return w.zero;
+            if (!ckpt) { *stride = hstride; return hbase + (size_t)t * g.level; }
+            if (t >= t0) { *stride = (size_t)(K - 1) * g.level; return w.seg_hist + (size_t)(t - t0) * g.level; }
+            const int j = t0 / K;  // t is t0-1 or t0-2: the checkpoint pair in front of segment j
+            *stride = ck_stride;
+            return ck_base + ((size_t)(j - 1) * 2 + (t - (t0 - 2))) * g.level;
+        };
+        for (int seg = nseg - 1; seg >= 0; --seg) {
+            const int t0 = ckpt ? seg * K : 0, t1 = ckpt ? std::min(nt, t0 + K) : nt;
+            if (ckpt) {
+                // recompute p_{t0} .. p_{t1-2} from the checkpoint pair (zeros for the first segment)
+                for (int t = t0; t <= t1 - 2; ++t) {
+                    FwdArgs f;
+                    f.p1 = forward_level(t - 1, t0, &f.ss_p1);
+                    f.p0 = forward_level(t - 2, t0, &f.ss_p0);
+                    f.out = const_cast<float *>(forward_level(t, t0, &f.ss_out));
+                    f.alpha = w.alpha + (size_t)b0 * g.level;
+                    f.kap = w.kap + (size_t)b0 * (g.nbc + 1);
+                    f.beta_src = w.beta_src + (size_t)b0 * g.ns;
+                    f.isx = p.d_isx; f.rec_ptr = p.d_rec_ptr; f.rec_idx = p.d_rec_idx;
+                    f.seis = nullptr; f.it_out = 0;
+                    f.w_t = p.wavelet[t];
+                    launch_fwd_step(p, f, nb, st);
+                }
+            }
+            for (int t = t1 - 1; t >= t0; --t) {
+                AdjArgs a;
+                a.q1 = w.fields + (size_t)((t + 1) % 3) * w.chunk_level;
+                a.q2 = w.fields + (size_t)((t + 2) % 3) * w.chunk_level;
+                a.out = w.fields + (size_t)(t % 3) * w.chunk_level;
+                a.pm1 = forward_level(t - 1, t0, &a.ss_pm1);
+                a.alpha = w.alpha + (size_t)b0 * g.level;
+                a.kap = w.kap + (size_t)b0 * (g.nbc + 1);
+                a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
+                a.cot = (t % p.st == 0) ? cot + (size_t)b0 * g.ns * g.nt_out * g.nrec : nullptr;
+                a.it_out = t / p.st;
+                a.w_t = p.wavelet[t];
+                a.Ga = w.Ga + (size_t)b0 * g.level;
+                a.Gk = w.Gk + (size_t)b0 * g.level;
+                a.Gb = w.Gb + (size_t)b0 * g.ns;
+                launch_adj_step(p, a, nb, st);
+            }
         }
     }
     // (when g_planes > 1 but the per-level engine ran, only plane 0 of each model was accumulated into)

@@ -62,6 +62,7 @@ struct Plan {
     int engine = 0;         // 0 = auto, 1 = per-level kernels, 2 = cluster-resident time loop
     int cluster_size = 0;   // 0 = smallest cluster that fits
     int adj_cluster_size = 0;
+    int history_segment = 0;  // 0 = keep every level; K >= 3 = checkpoint pairs every K levels, recompute in the backward pass
 };
 
 // Cluster-resident forward time loop (kernels_cluster.cu).

@@ -61,19 +61,20 @@ class _WaveSolve(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[0]
         with torch.cuda.device(v.device):
             stream = torch.cuda.current_stream().cuda_stream
-            hist, hist_bytes, lease = None, 0, None
+            hist, hist_bytes, lease, segment = None, 0, None, 0
             if need_grad:
-                hist_bytes = plan.history_bytes(B, 0)
+                segment = op._choose_segment(plan, B, v.device)
+                hist_bytes = plan.history_bytes(B, segment)
                 lease = op._lease_history(hist_bytes, v.device)
                 hist = lease.buffer
             seis = torch.empty((B, plan.ns, plan.nt_out, plan.nrec), dtype=torch.float32, device=v.device)
             ws_bytes = plan.workspace_bytes(B)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
             plan.forward(v.data_ptr(), B, seis.data_ptr(), ws.data_ptr(), ws_bytes,
-                         hist.data_ptr() if hist is not None else None, hist_bytes, 0, stream)
+                         hist.data_ptr() if hist is not None else None, hist_bytes, segment, stream)
             op.last_launches = plan.last_launch_count()
         if need_grad:
-            ctx.op, ctx.plan, ctx.hist, ctx.hist_bytes = op, plan, lease, hist_bytes
+            ctx.op, ctx.plan, ctx.hist, ctx.hist_bytes, ctx.segment = op, plan, lease, hist_bytes, segment
             ctx.save_for_backward(v)
         return seis
 
@@ -94,7 +95,7 @@ class _WaveSolve(torch.autograd.Function):
             ws_bytes = plan.workspace_bytes(B)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
             plan.backward(v.data_ptr(), B, g.data_ptr(), grad_v.data_ptr(), ws.data_ptr(), ws_bytes,
-                          hist.data_ptr(), ctx.hist_bytes, 0, stream)
+                          hist.data_ptr(), ctx.hist_bytes, ctx.segment, stream)
             ctx.op.last_launches += plan.last_launch_count()
         ctx.hist = None  # first-order only, like every caller in the reference
         lease.release()  # hand the wavefield history back to the operator's arena
@@ -127,6 +128,7 @@ class FWIForward(nn.Module):
         self.ctx = _survey.complete_ctx(ctx, sample_spatial)
         self._plans = {}
         self._history_arena = {}
+        self._segment = None
         self._lock = threading.Lock()
         self.last_launches = 0
         self.options = {}
@@ -164,6 +166,25 @@ class FWIForward(nn.Module):
                     plan.set(k, v)
                 self._plans[key] = plan
         return plan
+
+    def set_history_segment(self, segment):
+        """Wavefield-history policy.  0 = keep every level (fastest; the default while it fits),
+        K >= 3 = keep a pair of levels every K levels and recompute K levels at a time in the backward pass
+        (memory / (K/2), one extra forward), None = automatic."""
+        self._segment = segment
+
+    def _choose_segment(self, plan, B, device):
+        seg = self._segment
+        if seg is None:
+            free, _total = torch.cuda.mem_get_info(device)
+            idle = sum(b.numel() for b in self._history_arena.get(str(device), []))
+            budget = 0.9 * (free + idle + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device))
+            plan.set("history_segment", 0)
+            seg = 0
+            if plan.history_bytes(B, 0) + plan.workspace_bytes(B) > budget:
+                seg = max(3, int(np.ceil(np.sqrt(2.0 * plan.nt))))   # minimises pairs + segment levels
+        plan.set("history_segment", seg)
+        return seg
 
     def _lease_history(self, nbytes, device):
         """A history buffer of at least nbytes on `device`, reused across iterations when idle."""
