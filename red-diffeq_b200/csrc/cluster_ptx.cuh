@@ -54,6 +54,39 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest fp32 results per
+// issue slot.  NOTE: ptxas contracts a packed mul feeding a packed add into FFMA2 even with explicit .rn, so the
+// bit-exact forward path only uses f2add (on operands that are not packed products); the adjoint uses all three.
+__device__ __forceinline__ float2 f2add(const float2 a, const float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2sub(const float2 a, const float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2mul(const float2 a, const float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2fma(const float2 a, const float2 b, const float2 c)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+
 // per-thread constants of the cluster-resident sweeps
 struct SweepThread {
     int x, la, lb;            // first column, local row range [la, lb)

@@ -67,17 +67,31 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
         if (th.edgeR) { r0 = eRp[r * P]; r1 = eRp[r * P + 1]; }
         const float e[8] = {l2, l1, w2.x, w2.y, w2.z, w2.w, r0, r1};
         float o[4];
+        // Two cells per instruction for the twelve additions of a cell (FADD2, IEEE round-to-nearest per lane, same
+        // association as the reference); the six multiplications stay scalar so that ptxas cannot contract them
+        // into FFMA2 (it does contract packed products, even with .rn) -- seismograms stay bit-identical.
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float kp = th.colsp[j] ? kapx[j] : kapz;  // columns override rows (solvers/pde.py:50-51)
-            const float alj = lane(al[r], j);
-            // fp32 addition is commutative, so marching upwards (w1 = row below) gives the same bits as (:79)
-            const float s1 = __fadd_rn(__fadd_rn(__fadd_rn(lane(w1, j), lane(w3, j)), e[j + 1]), e[j + 3]);
-            const float s2 = __fadd_rn(__fadd_rn(__fadd_rn(lane(w0, j), lane(w4, j)), e[j]), e[j + 4]);
-            const float lap = __fadd_rn(__fmul_rn(c2, s1), __fmul_rn(c3, s2));
-            const float t1 = __fsub_rn(__fadd_rn(2.0f, __fmul_rn(-5.0f, alj)), kp);  // temp1 (:69)
-            const float t2 = __fsub_rn(1.0f, kp);                                     // temp2 (:70)
-            o[j] = __fadd_rn(__fsub_rn(__fmul_rn(t1, e[j + 2]), __fmul_rn(t2, lane(old, j))), __fmul_rn(alj, lap));
+        for (int h = 0; h < 2; ++h) {
+            const int j = 2 * h;
+            const float2 up1 = h ? make_float2(w1.z, w1.w) : make_float2(w1.x, w1.y);
+            const float2 dn1 = h ? make_float2(w3.z, w3.w) : make_float2(w3.x, w3.y);
+            const float2 up2 = h ? make_float2(w0.z, w0.w) : make_float2(w0.x, w0.y);
+            const float2 dn2 = h ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);
+            const float2 oldp = h ? make_float2(old.z, old.w) : make_float2(old.x, old.y);
+            const float2 alp = h ? make_float2(al[r].z, al[r].w) : make_float2(al[r].x, al[r].y);
+            // (((p1[z-1] + p1[z+1]) + p1[x-1]) + p1[x+1]) and the same at distance 2   (:79; + is commutative)
+            const float2 s1 = f2add(f2add(f2add(up1, dn1), make_float2(e[j + 1], e[j + 2])), make_float2(e[j + 3], e[j + 4]));
+            const float2 s2 = f2add(f2add(f2add(up2, dn2), make_float2(e[j], e[j + 1])), make_float2(e[j + 4], e[j + 5]));
+            const float2 lap = f2add(make_float2(__fmul_rn(c2, s1.x), __fmul_rn(c2, s1.y)),
+                                     make_float2(__fmul_rn(c3, s2.x), __fmul_rn(c3, s2.y)));
+            const float2 kp = make_float2(th.colsp[j] ? kapx[j] : kapz, th.colsp[j + 1] ? kapx[j + 1] : kapz);
+            const float2 t1 = f2sub(f2add(make_float2(2.0f, 2.0f), make_float2(__fmul_rn(-5.0f, alp.x), __fmul_rn(-5.0f, alp.y))), kp);
+            const float2 t2 = f2sub(make_float2(1.0f, 1.0f), kp);
+            const float2 a1 = make_float2(__fmul_rn(t1.x, e[j + 2]), __fmul_rn(t1.y, e[j + 3]));
+            const float2 a2 = make_float2(__fmul_rn(t2.x, oldp.x), __fmul_rn(t2.y, oldp.y));
+            const float2 a3 = make_float2(__fmul_rn(alp.x, lap.x), __fmul_rn(alp.y, lap.y));
+            const float2 res = f2add(f2sub(a1, a2), a3);
+            o[j] = res.x; o[j + 1] = res.y;
         }
         const int lr = l0 + DIR * r;
         const float4 out = make_float4(o[0], o[1], o[2], o[3]);

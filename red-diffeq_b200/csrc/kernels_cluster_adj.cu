@@ -59,16 +59,25 @@ __device__ __forceinline__ void adj_sweep(float *__restrict__ smem, const int cu
         if (th.edgeR) { r0 = eRp[r * P]; r1 = eRp[r * P + 1]; }
         const float e[8] = {l2, l1, w2.x, w2.y, w2.z, w2.w, r0, r1};
         float o[4];
+        // two cells per instruction (FADD2 / FMUL2 / FFMA2); contraction is welcome here
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float kp = th.colsp[j] ? kapx[j] : kapz;
-            const float alj = lane(alv[r], j);
-            const float s1 = ((lane(w1, j) + lane(w3, j)) + e[j + 1]) + e[j + 3];
-            const float s2 = ((lane(w0, j) + lane(w4, j)) + e[j]) + e[j + 4];
-            const float lap = c2 * s1 + c3 * s2;
-            const float t1 = (2.0f - 5.0f * alj) - kp;
-            const float t2 = 1.0f - kp;
-            o[j] = (t1 * e[j + 2] - t2 * lane(old, j)) + alj * lap;
+        for (int h = 0; h < 2; ++h) {
+            const int j = 2 * h;
+            const float2 up1 = h ? make_float2(w1.z, w1.w) : make_float2(w1.x, w1.y);
+            const float2 dn1 = h ? make_float2(w3.z, w3.w) : make_float2(w3.x, w3.y);
+            const float2 up2 = h ? make_float2(w0.z, w0.w) : make_float2(w0.x, w0.y);
+            const float2 dn2 = h ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);
+            const float2 oldp = h ? make_float2(old.z, old.w) : make_float2(old.x, old.y);
+            const float2 alp = h ? make_float2(alv[r].z, alv[r].w) : make_float2(alv[r].x, alv[r].y);
+            const float2 cen = make_float2(e[j + 2], e[j + 3]);
+            const float2 s1 = f2add(f2add(f2add(up1, dn1), make_float2(e[j + 1], e[j + 2])), make_float2(e[j + 3], e[j + 4]));
+            const float2 s2 = f2add(f2add(f2add(up2, dn2), make_float2(e[j], e[j + 1])), make_float2(e[j + 4], e[j + 5]));
+            const float2 lap = f2fma(make_float2(c2, c2), s1, f2mul(make_float2(c3, c3), s2));
+            const float2 kp = make_float2(th.colsp[j] ? kapx[j] : kapz, th.colsp[j + 1] ? kapx[j + 1] : kapz);
+            const float2 t1 = f2sub(f2fma(make_float2(-5.0f, -5.0f), alp, make_float2(2.0f, 2.0f)), kp);
+            const float2 t2 = f2sub(make_float2(1.0f, 1.0f), kp);
+            const float2 res = f2fma(alp, lap, f2sub(f2mul(t1, cen), f2mul(t2, oldp)));
+            o[j] = res.x; o[j + 1] = res.y;
         }
         const int lr = l0 + DIR * r;
         const float4 out = make_float4(o[0], o[1], o[2], o[3]);
@@ -110,13 +119,22 @@ __device__ __forceinline__ void imaging_sweep(const float *__restrict__ smem, co
         float ga[4] = {Ga[r].x, Ga[r].y, Ga[r].z, Ga[r].w};
         float gk[4] = {Gk[r].x, Gk[r].y, Gk[r].z, Gk[r].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float pc = e[j + 2];
-            const float s1 = ((lane(v1, j) + lane(v3, j)) + e[j + 1]) + e[j + 3];
-            const float s2 = ((lane(v0, j) + lane(v4, j)) + e[j]) + e[j + 4];
-            const float lp = (c2 * s1 + c3 * s2) - 5.0f * pc;
-            ga[j] += lane(ut, j) * lp;
-            gk[j] += (lane(u1, j) - lane(ut, j)) * pc;
+        for (int h = 0; h < 2; ++h) {
+            const int j = 2 * h;
+            const float2 up1 = h ? make_float2(v1.z, v1.w) : make_float2(v1.x, v1.y);
+            const float2 dn1 = h ? make_float2(v3.z, v3.w) : make_float2(v3.x, v3.y);
+            const float2 up2 = h ? make_float2(v0.z, v0.w) : make_float2(v0.x, v0.y);
+            const float2 dn2 = h ? make_float2(v4.z, v4.w) : make_float2(v4.x, v4.y);
+            const float2 utp = h ? make_float2(ut.z, ut.w) : make_float2(ut.x, ut.y);
+            const float2 u1p = h ? make_float2(u1.z, u1.w) : make_float2(u1.x, u1.y);
+            const float2 pc = make_float2(e[j + 2], e[j + 3]);
+            const float2 s1 = f2add(f2add(f2add(up1, dn1), make_float2(e[j + 1], e[j + 2])), make_float2(e[j + 3], e[j + 4]));
+            const float2 s2 = f2add(f2add(f2add(up2, dn2), make_float2(e[j], e[j + 1])), make_float2(e[j + 4], e[j + 5]));
+            const float2 lp = f2fma(make_float2(c2, c2), s1, f2fma(make_float2(c3, c3), s2, f2mul(make_float2(-5.0f, -5.0f), pc)));
+            const float2 gan = f2fma(utp, lp, make_float2(ga[j], ga[j + 1]));
+            const float2 gkn = f2fma(f2sub(u1p, utp), pc, make_float2(gk[j], gk[j + 1]));
+            ga[j] = gan.x; ga[j + 1] = gan.y;
+            gk[j] = gkn.x; gk[j + 1] = gkn.y;
         }
         Ga[r] = make_float4(ga[0], ga[1], ga[2], ga[3]);
         Gk[r] = make_float4(gk[0], gk[1], gk[2], gk[3]);

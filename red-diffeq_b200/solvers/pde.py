@@ -129,6 +129,7 @@ class FWIForward(nn.Module):
         self._plans = {}
         self._history_arena = {}
         self._segment = None
+        self._segment_auto = {}
         self._lock = threading.Lock()
         self.last_launches = 0
         self.options = {}
@@ -175,7 +176,10 @@ class FWIForward(nn.Module):
 
     def _choose_segment(self, plan, B, device):
         seg = self._segment
-        if seg is None:
+        key = (id(plan), B)
+        if seg is None and key in self._segment_auto:   # decided once per (plan, batch): cudaMemGetInfo is slow
+            seg = self._segment_auto[key]
+        elif seg is None:
             free, _total = torch.cuda.mem_get_info(device)
             idle = sum(b.numel() for b in self._history_arena.get(str(device), []))
             budget = 0.9 * (free + idle + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device))
@@ -183,6 +187,7 @@ class FWIForward(nn.Module):
             seg = 0
             if plan.history_bytes(B, 0) + plan.workspace_bytes(B) > budget:
                 seg = max(3, int(np.ceil(np.sqrt(2.0 * plan.nt))))   # minimises pairs + segment levels
+            self._segment_auto[key] = seg
         plan.set("history_segment", seg)
         return seg
 
