@@ -36,7 +36,7 @@ namespace {
 //   * two sweep instantiations (down / up) still fit the instruction cache; four (x two buffer roles) did
 //     not (ncu: stall_no_instruction), so buffer roles are runtime base pointers.
 
-template <int RMAX, int PITCH, int DIR>
+template <int RMAX, int PITCH, int DIR, bool EXACT>
 __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cur, const int prv, const int kap_off,
                                           const int pitch_rt, const int l0, const SweepThread &th,
                                           const float4 (&al)[RMAX], const float (&kapx)[4], const HaloPush &hp,
@@ -82,15 +82,24 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             // (((p1[z-1] + p1[z+1]) + p1[x-1]) + p1[x+1]) and the same at distance 2   (:79; + is commutative)
             const float2 s1 = f2add(f2add(f2add(up1, dn1), make_float2(e[j + 1], e[j + 2])), make_float2(e[j + 3], e[j + 4]));
             const float2 s2 = f2add(f2add(f2add(up2, dn2), make_float2(e[j], e[j + 1])), make_float2(e[j + 4], e[j + 5]));
-            const float2 lap = f2add(make_float2(__fmul_rn(c2, s1.x), __fmul_rn(c2, s1.y)),
-                                     make_float2(__fmul_rn(c3, s2.x), __fmul_rn(c3, s2.y)));
             const float2 kp = make_float2(th.colsp[j] ? kapx[j] : kapz, th.colsp[j + 1] ? kapx[j + 1] : kapz);
-            const float2 t1 = f2sub(f2add(make_float2(2.0f, 2.0f), make_float2(__fmul_rn(-5.0f, alp.x), __fmul_rn(-5.0f, alp.y))), kp);
-            const float2 t2 = f2sub(make_float2(1.0f, 1.0f), kp);
-            const float2 a1 = make_float2(__fmul_rn(t1.x, e[j + 2]), __fmul_rn(t1.y, e[j + 3]));
-            const float2 a2 = make_float2(__fmul_rn(t2.x, oldp.x), __fmul_rn(t2.y, oldp.y));
-            const float2 a3 = make_float2(__fmul_rn(alp.x, lap.x), __fmul_rn(alp.y, lap.y));
-            const float2 res = f2add(f2sub(a1, a2), a3);
+            float2 res;
+            if (EXACT) {  // forward wavefield: one rounding per reference op, products never packed (see above)
+                const float2 lap = f2add(make_float2(__fmul_rn(c2, s1.x), __fmul_rn(c2, s1.y)),
+                                         make_float2(__fmul_rn(c3, s2.x), __fmul_rn(c3, s2.y)));
+                const float2 t1 = f2sub(f2add(make_float2(2.0f, 2.0f), make_float2(__fmul_rn(-5.0f, alp.x), __fmul_rn(-5.0f, alp.y))), kp);
+                const float2 t2 = f2sub(make_float2(1.0f, 1.0f), kp);
+                const float2 a1 = make_float2(__fmul_rn(t1.x, e[j + 2]), __fmul_rn(t1.y, e[j + 3]));
+                const float2 a2 = make_float2(__fmul_rn(t2.x, oldp.x), __fmul_rn(t2.y, oldp.y));
+                const float2 a3 = make_float2(__fmul_rn(alp.x, lap.x), __fmul_rn(alp.y, lap.y));
+                res = f2add(f2sub(a1, a2), a3);
+            } else {      // adjoint field: no bit-parity requirement, packed FMA throughout
+                const float2 cen = make_float2(e[j + 2], e[j + 3]);
+                const float2 lap = f2fma(make_float2(c2, c2), s1, f2mul(make_float2(c3, c3), s2));
+                const float2 t1 = f2sub(f2fma(make_float2(-5.0f, -5.0f), alp, make_float2(2.0f, 2.0f)), kp);
+                const float2 t2 = f2sub(make_float2(1.0f, 1.0f), kp);
+                res = f2fma(alp, lap, f2sub(f2mul(t1, cen), f2mul(t2, oldp)));
+            }
             o[j] = res.x; o[j + 1] = res.y;
         }
         const int lr = l0 + DIR * r;
@@ -101,7 +110,12 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
     }
 }
 
-template <int RMAX, int PITCH>
+// ADJ = false: forward wavefield p (source injection, receiver sampling -> seismograms, history of p).
+// ADJ = true : adjoint field in the u-variable, u = alpha*q: the recurrence is the same, so the same
+//              sweep runs it; level k of the loop is reverse time t = nt-1-k, the "source" is alpha * cotangent at the
+//              receiver cells, the history receives u_{nt-1} .. u_1 (slot k), and sum_t u_t[src] w_t is accumulated
+//              for the beta_dt term.  The imaging sums are formed afterwards by k_imaging from the two histories.
+template <int RMAX, int PITCH, bool ADJ>
 __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdArgs a, Grid g)
 {
     extern __shared__ __align__(128) float smem[];
@@ -165,7 +179,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     }
     // early halo pushes: the CTA's first / last two rows are marching rows 0,1 of their owner threads --
     // unless the source row is one of them (it is patched in the epilogue, after which it is sent)
-    const bool src_on_edge = g.isz - r0 >= 0 && g.isz - r0 < nrows && (g.isz - r0 < 2 || g.isz - r0 >= nrows - 2);
+    const int patched_row = (ADJ ? g.igz : g.isz) - r0;  // the row whose cells are modified in the epilogue
+    const bool src_on_edge = patched_row >= 0 && patched_row < nrows && (patched_row < 2 || patched_row >= nrows - 2);
     HaloPush hp;
     hp.early = false; hp.dst = 0; hp.cta = 0; hp.bar = 0;
     if (active && !src_on_edge) {
@@ -199,7 +214,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
 
     int shot_iter = 0;
     for (int shot = cid; shot < a.nshots; shot += ncl, ++shot_iter) {
-        const int b = shot / g.ns, s = shot - b * g.ns;
+        const int gshot = a.shot0 + shot;  // index into per-shot inputs/outputs other than the history of this launch
+        const int b = gshot / g.ns, s = gshot - b * g.ns;
         // p_{-1} = p_{-2} = 0 (halo rows included); sponge tables of this model
         for (int i = tid; i < 2 * slab; i += kClusterThreads) smem[i] = 0.0f;
         const float *kap_b = a.kap + (size_t)b * (g.nbc + 1);
@@ -223,7 +239,17 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
         int src_mask = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) src_mask |= (th.src_lr >= 0 && xc[j] == xs) ? (1 << j) : 0;
-        const float bsrc = a.beta_src[shot];
+        const float bsrc = ADJ ? 0.0f : a.beta_src[gshot];
+        // adjoint mode: alpha of the receiver-row cells, lane of the (non-image) source cell, beta_dt accumulator
+        float4 al_rec = zero4;
+        int src_lane = -1;
+        float gb = 0.0f;
+        if (ADJ) {
+            if (th.rec_lr >= 0) al_rec = ld4(a.alpha + (size_t)b * g.level + (size_t)(r0 + th.rec_lr) * pitch + th.x);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (th.src_lr >= 0 && th.x + j < g.nxp && th.x + j == xs) src_lane = j;
+        }
         __syncthreads();
         cluster_sync_all();  // shot boundary: every CTA has finished the previous shot and cleared its buffers
 
@@ -245,11 +271,29 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                 }
             }
             const int p0 = prv + 2 * pitch + th.x;
+            const int trev = a.nt - 1 - t;  // adjoint mode: the reverse-time level this iteration computes
+            float cot4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ADJ && th.rec_lr >= 0 && trev % a.st == 0) {  // fetched before the sweep, consumed after it
+                const float *gt = a.cot + ((size_t)gshot * g.nt_out + trev / a.st) * g.nrec;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    for (int k = s_rec_ptr[xc[j]]; k < s_rec_ptr[xc[j] + 1]; ++k) cot4[j] += gt[s_rec_idx[k]];
+            }
             if (warp_active) {
                 const uint64_t *push_bar = bars + 2 * pbuf + hp.bar;  // barrier of the buffer written now, at the receiver
-                if (rev) fwd_sweep<RMAX, PITCH, -1>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
-                else fwd_sweep<RMAX, PITCH, 1>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
-                if (src_mask != 0) {  // p[src] += beta_dt[src] * wavelet[t]   (solvers/pde.py:80-81)
+                if (rev) fwd_sweep<RMAX, PITCH, -1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
+                else fwd_sweep<RMAX, PITCH, 1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
+                if (ADJ) {
+                    if (th.rec_lr >= 0 && trev % a.st == 0) {  // u_t[rec] += alpha * g_t  (adjoint of the gather, :83)
+                        float4 v = ld4(smem + p0 + th.rec_lr * pitch);
+                        v.x += al_rec.x * cot4[0]; v.y += al_rec.y * cot4[1]; v.z += al_rec.z * cot4[2]; v.w += al_rec.w * cot4[3];
+                        st4(smem + p0 + th.rec_lr * pitch, v);
+                    }
+                    if (src_lane >= 0) {  // adjoint of the source injection (:81)
+                        const float4 v = ld4(smem + p0 + th.src_lr * pitch);
+                        gb += (src_lane == 0 ? v.x : src_lane == 1 ? v.y : src_lane == 2 ? v.z : v.w) * (wav_in_smem ? s_wav[trev] : a.wavelet[trev]);
+                    }
+                } else if (src_mask != 0) {  // p[src] += beta_dt[src] * wavelet[t]   (solvers/pde.py:80-81)
                     const float src_add = __fmul_rn(bsrc, wav_in_smem ? s_wav[t] : a.wavelet[t]);
                     float4 v = ld4(smem + p0 + th.src_lr * pitch);
                     if (src_mask & 1) v.x = __fadd_rn(v.x, src_add);
@@ -258,8 +302,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                     if (src_mask & 8) v.w = __fadd_rn(v.w, src_add);
                     st4(smem + p0 + th.src_lr * pitch, v);
                 }
-                if (th.rec_lr >= 0 && t % a.st == 0) {  // sampled after injection (solvers/pde.py:82-83)
-                    float *seis_t = a.seis + ((size_t)shot * g.nt_out + t / a.st) * g.nrec;
+                if (!ADJ && th.rec_lr >= 0 && t % a.st == 0) {  // sampled after injection (solvers/pde.py:82-83)
+                    float *seis_t = a.seis + ((size_t)gshot * g.nt_out + t / a.st) * g.nrec;
                     const float4 v = ld4(smem + p0 + th.rec_lr * pitch);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -287,6 +331,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                            smem + prv + 2 * pitch, (uint32_t)(nrows * pitch * sizeof(float)));
         };
         for (int t = 0, cur = 0; t < a.nt; ++t, cur = slab - cur) level(t, cur, slab - cur);
+        if (ADJ && src_lane >= 0) {
+            const float4 alv = ld4(a.alpha + (size_t)b * g.level + (size_t)(r0 + th.src_lr) * pitch + th.x);
+            a.Gb[gshot] = gb / (src_lane == 0 ? alv.x : src_lane == 1 ? alv.y : src_lane == 2 ? alv.z : alv.w);
+        }
         if (a.hist != nullptr && tid == 0) bulk_wait_read();
         __syncthreads();
     }
@@ -320,10 +368,10 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg)
     return false;
 }
 
-template <int PITCH>
+template <int PITCH, bool ADJ>
 static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
 {
-    auto kernel = k_fwd_cluster<kClusterRowsMax, PITCH>;
+    auto kernel = k_fwd_cluster<kClusterRowsMax, PITCH, ADJ>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
     if (e != cudaSuccess) return e;
     a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
@@ -353,10 +401,11 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
 
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
 {
+    const bool adj = a.adj_mode != 0;
     switch (p.g.pitch) {  // production grids get immediate row offsets (OpenFWI 310+2, Marmousi/Overthrust 430+2)
-        case 312: return launch_fwd_cluster_t<312>(p, cc, a, st);
-        case 432: return launch_fwd_cluster_t<432>(p, cc, a, st);
-        default: return launch_fwd_cluster_t<0>(p, cc, a, st);
+        case 312: return adj ? launch_fwd_cluster_t<312, true>(p, cc, a, st) : launch_fwd_cluster_t<312, false>(p, cc, a, st);
+        case 432: return adj ? launch_fwd_cluster_t<432, true>(p, cc, a, st) : launch_fwd_cluster_t<432, false>(p, cc, a, st);
+        default: return adj ? launch_fwd_cluster_t<0, true>(p, cc, a, st) : launch_fwd_cluster_t<0, false>(p, cc, a, st);
     }
 }
 

@@ -72,6 +72,9 @@ struct Workspace {
     int nb = 0;
     int g_planes = 1;
     float *seg_hist = nullptr;
+    bool split = false;
+    int u_chunk = 0;
+    float *u_hist = nullptr;
 };
 
 Workspace carve(const Plan &p, int B, void *base)
@@ -96,8 +99,11 @@ Workspace carve(const Plan &p, int B, void *base)
     w.fields = (float *)take(3 * w.chunk_level * 4);
     w.zero = (float *)take(w.chunk_level * 4);
     ClusterConfig acc;
-    // per-shot imaging planes for the cluster adjoint; checkpointed histories run on the per-level engine
-    w.g_planes = (p.engine != 1 && p.history_segment == 0 && adj_cluster_config(p, &acc)) ? g.ns : 1;
+    // split adjoint (cluster u-field kernel + streaming imaging kernel) whenever the forward cluster kernel fits;
+    // else the fused cluster adjoint; checkpointed histories run on the per-level engine
+    const bool cluster_ok = p.engine != 1 && p.history_segment == 0;
+    w.split = cluster_ok && p.adj_mode == 0 && cluster_config(p, &acc);
+    w.g_planes = (w.split || (cluster_ok && adj_cluster_config(p, &acc))) ? g.ns : 1;  // per-shot imaging planes
     w.Ga = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gk = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gb = (float *)take((size_t)B * g.ns * 4);
@@ -105,6 +111,16 @@ Workspace carve(const Plan &p, int B, void *base)
     w.vel_part = (double *)take((size_t)B * kMinBlocks * 8);
     // checkpoint mode: the levels of one segment of one chunk, recomputed during the backward pass
     w.seg_hist = p.history_segment > 0 ? (float *)take(w.chunk_level * (size_t)(p.history_segment - 1) * 4) : nullptr;
+    // split adjoint: adjoint-field history of one chunk of shots
+    w.u_chunk = 0;
+    if (w.split) {
+        const int nshots = B * g.ns;
+        w.u_chunk = p.u_chunk_shots > 0 ? p.u_chunk_shots : 66;  // two waves of 33 four-CTA clusters ...
+        if (w.u_chunk > nshots) w.u_chunk = nshots;
+        const int nchunks = (nshots + w.u_chunk - 1) / w.u_chunk;
+        w.u_chunk = (nshots + nchunks - 1) / nchunks;              // ... evened out over the chunks
+        w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)std::max(p.nt - 1, 1) * g.level * 4);
+    }
     w.bytes = off;
     return w;
 }
@@ -253,6 +269,8 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "use_graph") { p->use_graph = value != 0; }
     else if (k == "engine") { if (value < 0 || value > 2) goto bad; p->engine = (int)value; }
     else if (k == "history_segment") { if (value < 0 || value == 1 || value == 2) goto bad; p->history_segment = (int)value; }
+    else if (k == "adj_mode") { if (value < 0 || value > 1) goto bad; p->adj_mode = (int)value; }
+    else if (k == "u_chunk_shots") { if (value < 0) goto bad; p->u_chunk_shots = (int)value; }
     else if (k == "cluster_size") { if (value < 0 || value > 8) goto bad; p->cluster_size = (int)value; }
     else if (k == "adj_cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->adj_cluster_size = (int)value; }
     else { set_error("unknown option " + k); return RDFWI_EINVAL; }
@@ -273,6 +291,8 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
     else if (k == "use_graph") *out = p->use_graph;
     else if (k == "engine") *out = p->engine;
     else if (k == "history_segment") *out = p->history_segment;
+    else if (k == "adj_mode") *out = p->adj_mode;
+    else if (k == "adj_split") { ClusterConfig cc; *out = (p->engine != 1 && p->history_segment == 0 && p->adj_mode == 0 && cluster_config(*p, &cc)) ? 1 : 0; }
     else if (k == "cluster_size") *out = p->cluster_size;
     else if (k == "cluster_size_used") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cc.C : 0; }
     else if (k == "adj_cluster_size_used") { ClusterConfig cc; *out = adj_cluster_config(*p, &cc) ? cc.C : 0; }
@@ -416,6 +436,24 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     const bool ckpt = segment > 0;
     RD_CUDA(cudaMemsetAsync(w.Gb, 0, (size_t)B * g.ns * sizeof(float), st));
     ClusterConfig cc;
+    if (!ckpt && w.split && cluster_config(p, &cc)) {
+        // split adjoint: per chunk of shots, (1) the cluster-resident kernel runs the adjoint field in the u-variable
+        // and streams it to HBM, (2) a streaming kernel forms the imaging sums from the two histories
+        const int nshots = B * g.ns;
+        for (int s0 = 0; s0 < nshots; s0 += w.u_chunk) {
+            const int n = std::min(w.u_chunk, nshots - s0);
+            ClusterFwdArgs a{};
+            a.alpha = w.alpha; a.kap = w.kap; a.beta_src = w.beta_src;
+            a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx; a.wavelet = p.d_wavelet;
+            a.seis = nullptr; a.hist = w.u_hist;
+            a.nshots = n; a.nt = nt; a.st = p.st;
+            a.shot0 = s0; a.adj_mode = 1; a.cot = cot; a.Gb = w.Gb;
+            RD_CUDA(launch_fwd_cluster(p, cc, a, st));
+            RD_CUDA(launch_imaging(p, hist, w.u_hist, w.alpha, w.Ga, w.Gk, s0, n, st));
+        }
+        RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
+        return RDFWI_OK;
+    }
     if (!ckpt && w.g_planes > 1 && adj_cluster_config(p, &cc)) {
         // cluster-resident reverse-time loop: one launch for all shots and all levels
         ClusterAdjArgs a{};

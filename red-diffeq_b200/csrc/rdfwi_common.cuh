@@ -62,6 +62,8 @@ struct Plan {
     int engine = 0;         // 0 = auto, 1 = per-level kernels, 2 = cluster-resident time loop
     int cluster_size = 0;   // 0 = smallest cluster that fits
     int adj_cluster_size = 0;
+    int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused k_adj_cluster
+    int u_chunk_shots = 0;    // shots whose adjoint-field history is in flight at once in split mode (0 = auto)
     int history_segment = 0;  // 0 = keep every level; K >= 3 = checkpoint pairs every K levels, recompute in the backward pass
 };
 
@@ -75,8 +77,12 @@ struct ClusterFwdArgs {
     const int *rec_idx;
     const float *wavelet;   // (nt) device
     float *seis;            // (B*ns, nt_out, nrec)
-    float *hist;            // [shot][t][z][x], t = 0..nt-2, or nullptr
+    float *hist;            // [shot][t][z][x], t = 0..nt-2, or nullptr (indexed by the launch-local shot)
     int nshots, nt, st;
+    int shot0;              // global index of the launch's first shot (seis / cot / Gb / model lookup)
+    int adj_mode;           // 0 = forward wavefield, 1 = adjoint field in the u-variable (see k_fwd_cluster)
+    const float *cot;       // adjoint mode: (B*ns, nt_out, nrec) cotangent of the seismograms
+    float *Gb;              // adjoint mode: (B*ns) sum_t u_t[src] w_t / alpha_src
     int slabrows, ngroups, wav_smem;  // filled by launch_fwd_cluster from the ClusterConfig
 };
 
@@ -158,6 +164,9 @@ cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFw
 // kernels_cluster_adj.cu
 bool adj_cluster_config(const Plan &p, ClusterConfig *cfg);
 cudaError_t launch_adj_cluster(const Plan &p, const ClusterConfig &cc, ClusterAdjArgs a, cudaStream_t st);
+// kernels_imaging.cu: zero-lag imaging sums of `nshots` shots from the forward history and the adjoint-field history
+cudaError_t launch_imaging(const Plan &p, const float *phist, const float *uhist, const float *alpha, float *Ga, float *Gk,
+                           int shot0, int nshots, cudaStream_t st);
 // kernels_epilogue.cu  (planes = imaging planes per model: 1 for the per-level engine, ns for the cluster engine)
 cudaError_t launch_gradient_epilogue(const Plan &p, const float *v, int B, const float *Ga, const float *Gk,
                                      const float *Gb, int planes, const int *argmin, float *fold_tmp,

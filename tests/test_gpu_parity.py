@@ -61,13 +61,16 @@ def test_gradient_matches_reference(golden):
 @pytest.mark.parametrize("name", ["tiny_default", "tiny_custom", "tiny_half_receivers"])
 @pytest.mark.parametrize("rows", [1, 2, 4])
 @pytest.mark.parametrize("chunk", [0, 1])
-@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("engine", ["per-level", "cluster-split", "cluster-fused"])
 def test_kernel_variants_agree_with_oracle(name, rows, chunk, engine, oracle):
-    if engine == 2 and (rows != 1 or chunk != 0):
+    if engine != "per-level" and (rows != 1 or chunk != 0):
         pytest.skip("rows/chunk only affect the per-level engine")
     g = Golden(name)
     op = _op(g)
-    op.set_option("engine", engine)
+    op.set_option("engine", 1 if engine == "per-level" else 2)
+    op.set_option("adj_mode", 1 if engine == "cluster-fused" else 0)   # split (default) or fused cluster adjoint
+    if engine == "cluster-split":
+        op.set_option("u_chunk_shots", 2)                                 # several chunks even on the tiny cases
     op.set_option("rows_per_thread", rows)
     op.set_option("adj_rows_per_thread", 1 if rows == 1 else 2)
     op.set_option("chunk_models", chunk)
