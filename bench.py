@@ -44,10 +44,14 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the `ncu --set full`
 # capture of the same workload committed under profiles/ (None = not captured for this workload)
 NCU_TRAFFIC_BYTES = {
-    # profiles/ncu_adj_cluster_r1_full_b64.txt: 123.85 GB read + 0.28 GB written by the one k_adj_cluster launch
-    ("openfwi_b64", "adjoint"): 124.13e9,
-    # profiles/ncu_fwd_cluster_r1_v5.txt (8 models, 200 levels: 3.03 GB written) scaled to 64 models x 999 stored levels
-    ("openfwi_b64", "forward"): 121.8e9,
+    # per launch, from profiles/launches_r1_split_b64.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum on
+    # the bench command): the forward launch writes the 123.7 GB history; each of the 5 adjoint-field launches writes a
+    # 64-shot u history; each imaging launch reads both histories of its 64 shots
+    ("openfwi_b64", "forward"): 123.8e9,
+    ("openfwi_b64", "adjoint_field"): 24.7e9,
+    ("openfwi_b64", "imaging"): 55.7e9,
+    # fused cluster adjoint (adj_mode=1), profiles/ncu_adj_cluster_r1_full_b64.txt
+    ("openfwi_b64", "adjoint_loop"): 124.13e9,
 }
 
 
@@ -265,6 +269,7 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     barrier()
+    op._plan_for(nz, nx, dev).set("timing", 1)   # library-side CUDA events per kernel class, inside the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -275,6 +280,9 @@ def main():
     t_stop.record()
     barrier()
     elapsed_ms = t_start.elapsed_time(t_stop)
+    kernel_us = {k: op._plan_for(nz, nx, dev).get("us_" + k) for k in ("forward", "adjoint_field", "imaging", "adjoint_loop")}
+    kernel_n = {k: op._plan_for(nz, nx, dev).get("n_" + k) for k in ("forward", "adjoint_field", "imaging", "adjoint_loop")}
+    op._plan_for(nz, nx, dev).set("timing", 0)
     fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     adj_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
     launches_f, launches_b = evs[-1][3], evs[-1][4]
@@ -308,18 +316,42 @@ def main():
         value = pairs_total / (ms_per_step * 1e-3)
         e2e_value = pairs_total / (e2e_ms / args.steps * 1e-3)
         peak, peak_src = measured_peak_gbs()
-        # dominant kernel = the adjoint time loop: k_adj_cluster (cluster-resident engine: ONE launch runs all
-        # levels of all shots) or k_adj_step (per-level engine: one launch per level per chunk of models)
+        # Per-kernel-class device times come from CUDA events the library records on the launch stream around
+        # each class of launches inside the timed region (rdfwi_plan_set "timing").
         plan = op._plan_for(nz, nx, dev)
         eng = op.options.get("engine", 0)
-        adj_cluster = eng != 1 and plan.get("adj_cluster_size_used") > 0
-        fwd_cluster = eng != 1 and plan.get("cluster_size_used") > 0
-        step_launches_b = max(launches_b - 7, 1)      # minus prologue (3) + epilogue (4) launches
-        adj_launch_s = adj_ms * 1e-3 / step_launches_b
-        bytes_per_launch = ALGO_BYTES_ADJ * cells_level * nt / step_launches_b
-        achieved = bytes_per_launch / adj_launch_s / 1e9
-        step_launches_f = max(launches_f - 3, 1)
-        fwd_achieved = ALGO_BYTES_FWD * cells_level * nt / (fwd_ms * 1e-3) / 1e9
+        fwd_cluster = eng != 1 and plan.get("cluster_size_used") > 0 and plan.get("history_segment") == 0
+        adj_split = plan.get("adj_split") == 1
+        adj_cluster = (not adj_split) and eng != 1 and plan.get("adj_cluster_size_used") > 0 and plan.get("history_segment") == 0
+        us = {k: kernel_us[k] / args.steps for k in kernel_us}
+        n = {k: kernel_n[k] // args.steps for k in kernel_n}
+        cell_updates = float(cells_level) * nt
+        kernels = {
+            "forward": {"kernel": "k_fwd_cluster<EXACT>" if fwd_cluster else "k_fwd_step", "us": us["forward"],
+                        "launches": n["forward"] if fwd_cluster else launches_f - 3, "algo_bytes": ALGO_BYTES_FWD * cell_updates},
+        }
+        if adj_split:
+            # the adjoint's 16 B / cell-update split as: adjoint-field kernel (read u_{t+1}, u_{t+2}, write u_t = 12 B; all of
+            # it stays in shared memory, only the 4 B history write reaches HBM) + imaging kernel (read p_{t-1}, u_t = 8 B,
+            # of which u_t is traffic the fused formulation would not have: counted, it is what the kernel really streams)
+            kernels["adjoint_field"] = {"kernel": "k_fwd_cluster<ADJ>", "us": us["adjoint_field"], "launches": n["adjoint_field"],
+                                        "algo_bytes": 12.0 * cell_updates}
+            kernels["imaging"] = {"kernel": "k_imaging", "us": us["imaging"], "launches": n["imaging"],
+                                  "algo_bytes": 8.0 * float(cells_level) * (nt - 1)}
+        else:
+            kernels["adjoint_loop"] = {"kernel": "k_adj_cluster" if adj_cluster else "k_adj_step", "us": us["adjoint_loop"],
+                                       "launches": n["adjoint_loop"] if adj_cluster else launches_b - 7,
+                                       "algo_bytes": ALGO_BYTES_ADJ * cell_updates}
+        peak, peak_src = measured_peak_gbs()
+        for kk in kernels.values():
+            kk["achieved_gbs"] = kk["algo_bytes"] / (kk["us"] * 1e-6) / 1e9 if kk["us"] > 0 else None
+            kk["avg_launch_us"] = kk["us"] / max(kk["launches"], 1)
+        for kk in kernels.values():
+            kk["frac"] = kk["achieved_gbs"] / peak if kk["achieved_gbs"] else None
+        dom_key = max(kernels, key=lambda q: kernels[q]["us"])
+        dom = kernels[dom_key]
+        fwd_achieved = ALGO_BYTES_FWD * cell_updates / (fwd_ms * 1e-3) / 1e9
+        adj_achieved = ALGO_BYTES_ADJ * cell_updates / (adj_ms * 1e-3) / 1e9
         line = {
             "metric": "FD cell-updates/s (fwd+adjoint)", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -330,22 +362,24 @@ def main():
                        "l2_policy": "working set (wavefield history %.1f GB) far exceeds the 126 MB L2; no flush needed"
                                     % (op._plan_for(nz, nx, dev).history_bytes(B) / 1e9),
                        "engine": {"forward": "cluster-resident (C=%d)" % plan.get("cluster_size_used") if fwd_cluster else "per-level",
-                                  "adjoint": "cluster-resident (C=%d)" % plan.get("adj_cluster_size_used") if adj_cluster else "per-level"},
+                                  "adjoint": ("split: cluster-resident adjoint field (C=%d) + streaming imaging" % plan.get("cluster_size_used")) if adj_split
+                                  else ("cluster-resident fused (C=%d)" % plan.get("adj_cluster_size_used") if adj_cluster else "per-level")},
                        "options": dict(op.options)},
             "e2e": {"value": e2e_value, "unit": "pairs/s",
                     "h2d_bytes_per_step": int(vn_host.numel() * 4 + y_host.numel() * 4),
                     "d2h_bytes_per_step": int(grad_host.numel() * 4 + loss_host.numel() * 4)},
             "gpu_launches": int((launches_f + launches_b) * args.steps),
-            "roofline": {"bound": "hbm", "kernel": "k_adj_cluster" if adj_cluster else "k_adj_step", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "adjoint")), "peak_source": peak_src,
-                         "algorithmic_bytes_per_cell_update": ALGO_BYTES_ADJ,
-                         "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": adj_launch_s * 1e6,
-                         "launches_per_step": step_launches_b,
-                         "forward": {"kernel": "k_fwd_cluster" if fwd_cluster else "k_fwd_step", "achieved": fwd_achieved,
-                                     "frac": fwd_achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get((args.workload, "forward")),
-                                     "algorithmic_bytes_per_cell_update": ALGO_BYTES_FWD,
-                                     "avg_launch_us": fwd_ms * 1e3 / step_launches_f, "launches_per_step": step_launches_f},
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": dom["frac"], "traffic": NCU_TRAFFIC_BYTES.get((args.workload, dom_key)),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algo_bytes"] / max(dom["launches"], 1),
+                         "avg_launch_us": dom["avg_launch_us"], "launches_per_step": dom["launches"],
+                         "share_of_step": dom["us"] * 1e-3 / ms_per_step,
+                         "kernels": {k: {"kernel": v["kernel"], "ms_per_step": v["us"] * 1e-3, "launches_per_step": v["launches"],
+                                         "algorithmic_GB_per_step": v["algo_bytes"] / 1e9, "achieved_gbs": v["achieved_gbs"],
+                                         "frac": v["frac"], "traffic": NCU_TRAFFIC_BYTES.get((args.workload, k))}
+                                     for k, v in kernels.items()},
+                         # SURVEY.md 8(d) aggregates: 12 B forward, 16 B adjoint (both adjoint kernels together), 28 B pair
+                         "forward_frac": fwd_achieved / peak, "adjoint_frac": adj_achieved / peak,
                          "pair_frac": (ALGO_BYTES_PAIR * pairs_rank / ((fwd_ms + adj_ms) * 1e-3) / 1e9) / peak},
             "phase_ms": {"forward": fwd_ms, "adjoint": adj_ms},
             "clocks": clocks,

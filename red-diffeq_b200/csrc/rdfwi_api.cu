@@ -44,6 +44,44 @@ struct DeviceGuard {
 
 size_t align_up(size_t n, size_t a) { return (n + a - 1) / a * a; }
 
+// RAII CUDA-event bracket around the launches of one kernel class (only when the plan's "timing" option is on)
+struct Timed {
+    Plan *p;
+    cudaStream_t st;
+    Plan::Span span{};
+    bool on;
+    Timed(const Plan &plan, int kind, cudaStream_t stream) : p(const_cast<Plan *>(&plan)), st(stream), on(plan.timing != 0)
+    {
+        if (!on) return;
+        span.kind = kind;
+        on = cudaEventCreate(&span.a) == cudaSuccess && cudaEventCreate(&span.b) == cudaSuccess;
+        if (on) cudaEventRecord(span.a, st);
+    }
+    ~Timed()
+    {
+        if (!on) return;
+        cudaEventRecord(span.b, st);
+        p->spans.push_back(span);
+    }
+};
+
+// sum (microseconds) and count of the recorded spans of one kind; synchronises on their events
+void span_total(Plan *p, int kind, double *us, int *count)
+{
+    *us = 0.0; *count = 0;
+    for (const Plan::Span &s : p->spans) {
+        if (s.kind != kind) continue;
+        float ms = 0.f;
+        if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { *us += 1e3 * ms; ++*count; }
+    }
+}
+
+void clear_spans(Plan *p)
+{
+    for (const Plan::Span &s : p->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    p->spans.clear();
+}
+
 int chunk_models(const Plan &p, int B)
 {
     int nb = p.chunk_models;
@@ -253,6 +291,7 @@ int rdfwi_plan_destroy(rdfwi_plan plan)
     if (!plan) return RDFWI_OK;
     Plan *p = reinterpret_cast<Plan *>(plan);
     DeviceGuard guard(p->device);
+    clear_spans(p);
     cudaFree(p->d_isx); cudaFree(p->d_rec_ptr); cudaFree(p->d_rec_idx); cudaFree(p->d_r2); cudaFree(p->d_dkap); cudaFree(p->d_wavelet);
     delete p;
     return RDFWI_OK;
@@ -270,6 +309,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "engine") { if (value < 0 || value > 2) goto bad; p->engine = (int)value; }
     else if (k == "history_segment") { if (value < 0 || value == 1 || value == 2) goto bad; p->history_segment = (int)value; }
     else if (k == "adj_mode") { if (value < 0 || value > 1) goto bad; p->adj_mode = (int)value; }
+    else if (k == "timing") { clear_spans(p); p->timing = value != 0; }  // (re)starts the per-kernel-class timers
     else if (k == "u_chunk_shots") { if (value < 0) goto bad; p->u_chunk_shots = (int)value; }
     else if (k == "cluster_size") { if (value < 0 || value > 8) goto bad; p->cluster_size = (int)value; }
     else if (k == "adj_cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->adj_cluster_size = (int)value; }
@@ -292,6 +332,15 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
     else if (k == "engine") *out = p->engine;
     else if (k == "history_segment") *out = p->history_segment;
     else if (k == "adj_mode") *out = p->adj_mode;
+    else if (k.rfind("us_", 0) == 0 || k.rfind("n_", 0) == 0) {
+        const bool want_us = k[0] == 'u';
+        const std::string what = k.substr(want_us ? 3 : 2);
+        const int kind = what == "forward" ? 0 : what == "adjoint_field" ? 1 : what == "imaging" ? 2 : what == "adjoint_loop" ? 3 : -1;
+        if (kind < 0) { set_error("unknown timer " + k); return RDFWI_EINVAL; }
+        double us; int n;
+        span_total(p, kind, &us, &n);
+        *out = want_us ? (int64_t)(us + 0.5) : n;
+    }
     else if (k == "adj_split") { ClusterConfig cc; *out = (p->engine != 1 && p->history_segment == 0 && p->adj_mode == 0 && cluster_config(*p, &cc)) ? 1 : 0; }
     else if (k == "cluster_size") *out = p->cluster_size;
     else if (k == "cluster_size_used") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cc.C : 0; }
@@ -360,10 +409,12 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
         a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx; a.wavelet = p.d_wavelet;
         a.seis = seis; a.hist = hist;
         a.nshots = B * g.ns; a.nt = nt; a.st = p.st;
+        Timed timed(p, 0, st);
         RD_CUDA(launch_fwd_cluster(p, cc, a, st));
         return RDFWI_OK;
     }
     if (p.engine == 2 && !ckpt) { set_error("engine=2 (cluster-resident) requested but the grid does not fit a cluster"); return RDFWI_EINVAL; }
+    Timed timed_loop(p, 0, st);
     if (hist) RD_CUDA(cudaMemsetAsync(w.zero, 0, w.chunk_level * sizeof(float), st));
     const int K = segment;
     const size_t ck_stride = ckpt ? (size_t)(num_segments(p, K) - 1) * 2 * g.level : 0;  // shot stride of the checkpoints
@@ -448,7 +499,11 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
             a.seis = nullptr; a.hist = w.u_hist;
             a.nshots = n; a.nt = nt; a.st = p.st;
             a.shot0 = s0; a.adj_mode = 1; a.cot = cot; a.Gb = w.Gb;
-            RD_CUDA(launch_fwd_cluster(p, cc, a, st));
+            {
+                Timed timed(p, 1, st);
+                RD_CUDA(launch_fwd_cluster(p, cc, a, st));
+            }
+            Timed timed(p, 2, st);
             RD_CUDA(launch_imaging(p, hist, w.u_hist, w.alpha, w.Ga, w.Gk, s0, n, st));
         }
         RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
@@ -460,7 +515,10 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
         a.alpha = w.alpha; a.kap = w.kap; a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
         a.wavelet = p.d_wavelet; a.cot = cot; a.hist = hist; a.Ga = w.Ga; a.Gk = w.Gk; a.Gb = w.Gb;
         a.nshots = B * g.ns; a.nt = nt; a.st = p.st;
-        RD_CUDA(launch_adj_cluster(p, cc, a, st));
+        {
+            Timed timed(p, 3, st);
+            RD_CUDA(launch_adj_cluster(p, cc, a, st));
+        }
         RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
         return RDFWI_OK;
     }
@@ -469,6 +527,7 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     const int K = segment;
     const int nseg = ckpt ? num_segments(p, K) : 1;
     const size_t ck_stride = ckpt ? (size_t)(nseg - 1) * 2 * g.level : 0;
+    Timed *timed_adj = new Timed(p, 3, st);
     RD_CUDA(cudaMemsetAsync(w.Ga, 0, (size_t)B * w.g_planes * g.level * sizeof(float), st));
     RD_CUDA(cudaMemsetAsync(w.Gk, 0, (size_t)B * w.g_planes * g.level * sizeof(float), st));
 
@@ -527,6 +586,7 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
             }
         }
     }
+    delete timed_adj;
     // (when g_planes > 1 but the per-level engine ran, only plane 0 of each model was accumulated into)
     RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, 1, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
     return RDFWI_OK;

@@ -64,6 +64,10 @@ struct Plan {
     int adj_cluster_size = 0;
     int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused k_adj_cluster
     int u_chunk_shots = 0;    // shots whose adjoint-field history is in flight at once in split mode (0 = auto)
+    // optional per-kernel-class timing with CUDA events on the caller's stream (rdfwi_plan_set "timing")
+    int timing = 0;
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;  // kind: 0 forward time loop, 1 adjoint-field time loop, 2 imaging, 3 fused / per-level adjoint loop
     int history_segment = 0;  // 0 = keep every level; K >= 3 = checkpoint pairs every K levels, recompute in the backward pass
 };
 
