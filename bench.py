@@ -39,6 +39,9 @@ WORKLOADS = {
     # configs[2]: ONE Marmousi-shaped model, 40 shots (the reference's 5 do not divide over 8 GPUs)
     # sharded over the ranks by ShardedFWIForward: strong scaling, one gradient all-reduce per step
     "marmousi_sharded": ("marmousi40", 70, 190, 1),
+    # configs[3]: Overthrust shape (= the Marmousi grid in the reference's configs) with a long record, nt = 4000
+    # (synthetic extension); run with --history-segment K to exercise wavefield checkpointing
+    "overthrust_long": ("overthrust4000", 70, 190, 8),
 }
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the `ncu --set full`
@@ -62,6 +65,8 @@ def make_ctx(kind):
     ctx = dict(synthetic.PDE_MARMOUSI)
     if kind == "marmousi40":
         ctx["ns"] = 40
+    if kind == "overthrust4000":
+        ctx["nt"] = 4000
     return ctx
 
 
@@ -180,6 +185,8 @@ def main():
     ap.add_argument("--nt", type=int, default=0, help="override time levels (debugging; invalidates the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (e.g. chunk_models=8)")
+    ap.add_argument("--history-segment", type=int, default=None,
+                    help="wavefield history policy: 0 = every level, K >= 3 = checkpoint every K levels (default: automatic)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -225,6 +232,8 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=")
         op.set_option(k, int(v))
+    if args.history_segment is not None:
+        op.set_history_segment(args.history_segment)
     pairs_rank = B * ns_local * nzp * nxp * nt
     cells_level = B * ns_local * nzp * nxp
 
@@ -360,7 +369,8 @@ def main():
                        "shots_on_rank0": ns_local, "nt": nt,
                        "padded_grid": [nzp, nxp], "pairs_per_step_per_gpu": pairs_rank,
                        "l2_policy": "working set (wavefield history %.1f GB) far exceeds the 126 MB L2; no flush needed"
-                                    % (op._plan_for(nz, nx, dev).history_bytes(B) / 1e9),
+                                    % (op._plan_for(nz, nx, dev).history_bytes(B, op._plan_for(nz, nx, dev).get("history_segment")) / 1e9),
+                       "history": ("checkpoint pairs every %d levels" % plan.get("history_segment")) if plan.get("history_segment") else "every level",
                        "engine": {"forward": "cluster-resident (C=%d)" % plan.get("cluster_size_used") if fwd_cluster else "per-level",
                                   "adjoint": ("split: cluster-resident adjoint field (C=%d) + streaming imaging" % plan.get("cluster_size_used")) if adj_split
                                   else ("cluster-resident fused (C=%d)" % plan.get("adj_cluster_size_used") if adj_cluster else "per-level")},

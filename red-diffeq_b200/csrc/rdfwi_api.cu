@@ -140,8 +140,21 @@ Workspace carve(const Plan &p, int B, void *base)
     // split adjoint (cluster u-field kernel + streaming imaging kernel) whenever the forward cluster kernel fits;
     // else the fused cluster adjoint; checkpointed histories run on the per-level engine
     const bool cluster_ok = p.engine != 1 && p.history_segment == 0;
+    const bool fused_ok = cluster_ok && adj_cluster_config(p, &acc);
     w.split = cluster_ok && p.adj_mode == 0 && cluster_config(p, &acc);
-    w.g_planes = (w.split || (cluster_ok && adj_cluster_config(p, &acc))) ? g.ns : 1;  // per-shot imaging planes
+    w.u_chunk = 0;
+    if (w.split) {
+        // shots whose adjoint-field history is in flight at once: two waves of 33 four-CTA clusters, evened out over the
+        // chunks, and at most ~40 GB of scratch; long records that leave less than a wave per chunk use the fused kernel
+        const int nshots = B * g.ns;
+        const double per_shot = (double)std::max(p.nt - 1, 1) * (double)g.level * sizeof(float);
+        int chunk = p.u_chunk_shots > 0 ? p.u_chunk_shots : std::min(66, std::max(1, (int)(40e9 / per_shot)));
+        chunk = std::min(chunk, nshots);
+        const int nchunks = (nshots + chunk - 1) / chunk;
+        w.u_chunk = (nshots + nchunks - 1) / nchunks;
+        if (p.u_chunk_shots == 0 && w.u_chunk < nshots && w.u_chunk < 24 && fused_ok) { w.split = false; w.u_chunk = 0; }
+    }
+    w.g_planes = (w.split || fused_ok) ? g.ns : 1;  // per-shot imaging planes
     w.Ga = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gk = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gb = (float *)take((size_t)B * g.ns * 4);
@@ -150,15 +163,7 @@ Workspace carve(const Plan &p, int B, void *base)
     // checkpoint mode: the levels of one segment of one chunk, recomputed during the backward pass
     w.seg_hist = p.history_segment > 0 ? (float *)take(w.chunk_level * (size_t)(p.history_segment - 1) * 4) : nullptr;
     // split adjoint: adjoint-field history of one chunk of shots
-    w.u_chunk = 0;
-    if (w.split) {
-        const int nshots = B * g.ns;
-        w.u_chunk = p.u_chunk_shots > 0 ? p.u_chunk_shots : 66;  // two waves of 33 four-CTA clusters ...
-        if (w.u_chunk > nshots) w.u_chunk = nshots;
-        const int nchunks = (nshots + w.u_chunk - 1) / w.u_chunk;
-        w.u_chunk = (nshots + nchunks - 1) / nchunks;              // ... evened out over the chunks
-        w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)std::max(p.nt - 1, 1) * g.level * 4);
-    }
+    if (w.split) w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)std::max(p.nt - 1, 1) * g.level * 4);
     w.bytes = off;
     return w;
 }
@@ -342,7 +347,7 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
         span_total(p, kind, &us, &n);
         *out = want_us ? (int64_t)(us + 0.5) : n;
     }
-    else if (k == "adj_split") { ClusterConfig cc; *out = (p->engine != 1 && p->history_segment == 0 && p->adj_mode == 0 && cluster_config(*p, &cc)) ? 1 : 0; }
+    else if (k == "adj_split") *out = p->last_split;
     else if (k == "cluster_size") *out = p->cluster_size;
     else if (k == "cluster_size_used") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cc.C : 0; }
     else if (k == "adj_cluster_size_used") { ClusterConfig cc; *out = adj_cluster_config(*p, &cc) ? cc.C : 0; }
@@ -488,6 +493,7 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     const bool ckpt = segment > 0;
     RD_CUDA(cudaMemsetAsync(w.Gb, 0, (size_t)B * g.ns * sizeof(float), st));
     ClusterConfig cc;
+    const_cast<Plan &>(p).last_split = (!ckpt && w.split) ? 1 : 0;
     if (!ckpt && w.split && cluster_config(p, &cc)) {
         // split adjoint: per chunk of shots, (1) the cluster-resident kernel runs the adjoint field in the u-variable
         // and streams it to HBM, (2) a streaming kernel forms the imaging sums from the two histories

@@ -63,6 +63,7 @@ struct Plan {
     int cluster_size = 0;   // 0 = smallest cluster that fits
     int adj_cluster_size = 0;
     int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused k_adj_cluster
+    int last_split = 0;       // whether the last rdfwi_backward ran the split adjoint (reported by rdfwi_plan_get "adj_split")
     int img_rows = 0;         // imaging kernel variant: 0/3 = one row per thread, 3 CTAs/SM (default, measured best: 57 ms);
                               // 1 = one row, 4 CTAs/SM (63 ms); 2 = two rows per thread, 2 CTAs/SM (64 ms)
     int u_chunk_shots = 0;    // shots whose adjoint-field history is in flight at once in split mode (0 = auto)

@@ -1,0 +1,43 @@
+"""GPU: the operator inside an inversion loop shaped like the reference's InversionEngine.optimize
+(core/inversion.py:42-92: Adam on a padded, normalised leaf `mu`, forward on the slice mu[:, :, 1:-1, 1:-1], masked L1
+data misfit per model, clamp to [-1, 1], cosine LR) -- without the diffusion regulariser, which stays on the stock
+PyTorch path and is out of scope here.  Checks drop-in behaviour, not convergence quality."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def test_adam_loop_reduces_the_data_misfit():
+    from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize
+    from red_diffeq_b200.utils import synthetic
+    ctx = dict(n_grid=24, nt=160, dx=10.0, dt=0.001, nbc=12, f=25.0, sz=10, gz=10, ng=24, ns=3)
+    dev = torch.device("cuda:0")
+    op = FWIForward(ctx, dev, normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none).to(dev)
+    assert callable(op)
+    B, nz, nx = 2, 20, 24
+    mu_true = torch.tensor(synthetic.velocity_models(B, nz, nx, seed=21), device=dev)
+    with torch.no_grad():
+        y = op(mu_true)                                        # observed data (no history kept under no_grad)
+    assert not y.requires_grad
+    mu0 = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(mu_true, (3, 3, 3, 3), mode="replicate"), 7, stride=1)  # smoothed start
+    mu = torch.nn.functional.pad(mu0, (1, 1, 1, 1), value=0.0).clone().requires_grad_(True)   # (B,1,nz+2,nx+2) like scripts/run_inversion.py:156
+    opt = torch.optim.Adam([mu], lr=0.03)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=12, eta_min=0.0)
+    mask = torch.ones_like(y)
+    losses = []
+    for _ in range(12):
+        x0 = mu + 1e-4 * torch.randn_like(mu)
+        pred = op(x0[:, :, 1:-1, 1:-1])
+        loss = ((y - pred).abs() * mask).sum(dim=(1, 2, 3)) / mask.sum(dim=(1, 2, 3)).clamp(min=1.0)
+        opt.zero_grad(set_to_none=True)
+        loss.sum().backward()
+        opt.step()
+        with torch.no_grad():
+            mu.data.clamp_(-1, 1)
+        sched.step()
+        losses.append(float(loss.sum()))
+    assert np.isfinite(losses).all()
+    assert losses[-1] < 0.7 * losses[0], losses
+    assert float(mu.grad[:, :, 0, :].abs().max()) == 0.0        # the padding ring gets no gradient from the data term
