@@ -351,7 +351,8 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg)
     if (groups_max < 1) return false;
     int max_smem = 0;
     if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device) != cudaSuccess) return false;
-    for (int C = 1; C <= 8; ++C) {
+    for (int C = 1; C <= 16; ++C) {
+        if (C > 8 && C != 16) continue;  // 1..8 are portable cluster sizes, 16 needs the non-portable opt-in
         if (p.cluster_size > 0 && C != p.cluster_size) continue;
         if (g.nzp / C < 2) break;
         const int maxrows = (g.nzp + C - 1) / C;
@@ -375,6 +376,10 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
     if (e != cudaSuccess) return e;
     a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
+    if (cc.C > 8) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
 
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];

@@ -175,19 +175,28 @@ class FWIForward(nn.Module):
         self._segment = segment
 
     def _choose_segment(self, plan, B, device):
+        """History policy of one forward/backward pair.  Automatic mode walks three tiers until the buffers fit the
+        free HBM: (1) every level + split adjoint (needs a scratch history of the adjoint field), (2) every level +
+        fused cluster adjoint (no scratch), (3) checkpointed history on the per-level engine."""
         seg = self._segment
         key = (id(plan), B)
         if seg is None and key in self._segment_auto:   # decided once per (plan, batch): cudaMemGetInfo is slow
-            seg = self._segment_auto[key]
+            seg, adj_mode = self._segment_auto[key]
+            if adj_mode is not None:
+                plan.set("adj_mode", adj_mode)
         elif seg is None:
             free, _total = torch.cuda.mem_get_info(device)
             idle = sum(b.numel() for b in self._history_arena.get(str(device), []))
             budget = 0.9 * (free + idle + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device))
+            seg, adj_mode = 0, None
             plan.set("history_segment", 0)
-            seg = 0
             if plan.history_bytes(B, 0) + plan.workspace_bytes(B) > budget:
-                seg = max(3, int(np.ceil(np.sqrt(2.0 * plan.nt))))   # minimises pairs + segment levels
-            self._segment_auto[key] = seg
+                if "adj_mode" not in self.options:
+                    adj_mode = 1
+                    plan.set("adj_mode", 1)
+                if adj_mode is None or plan.history_bytes(B, 0) + plan.workspace_bytes(B) > budget:
+                    seg = max(3, int(np.ceil(np.sqrt(2.0 * plan.nt))))   # minimises pairs + segment levels
+            self._segment_auto[key] = (seg, adj_mode)
         plan.set("history_segment", seg)
         return seg
 

@@ -36,14 +36,18 @@ def run_case(n, ns, B, nt, peak):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record(); s = op(vv); e[1].record(); s.backward(torch.ones_like(s)); e[2].record()
         return e
-    step(); torch.cuda.synchronize()
-    e = step(); torch.cuda.synchronize()
-    f_ms, a_ms = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+    step(); step(); torch.cuda.synchronize()
+    f_ms = a_ms = None
+    for _ in range(2):  # best of two timed evaluations
+        e = step(); torch.cuda.synchronize()
+        f, a = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+        if f_ms is None or f + a < f_ms + a_ms:
+            f_ms, a_ms = f, a
     pairs = B * ns * (n + 240) ** 2 * nt
     rate = pairs / ((f_ms + a_ms) * 1e-3)
     seg = plan.get("history_segment")
     eng_f = "cluster C=%d" % plan.get("cluster_size_used") if plan.get("cluster_size_used") and not seg else "per-level"
-    eng_a = "cluster C=%d" % plan.get("adj_cluster_size_used") if plan.get("adj_cluster_size_used") and not seg else "per-level"
+    eng_a = ("split" if plan.get("adj_split") else "cluster C=%d" % plan.get("adj_cluster_size_used")) if (plan.get("adj_split") or plan.get("adj_cluster_size_used")) and not seg else "per-level"
     op.release_memory()
     return dict(n=n, ns=ns, B=B, nt=nt, forward_ms=f_ms, adjoint_ms=a_ms, pairs_per_s=rate, frac=rate * 28 / (peak * 1e9),
                 engine_fwd=eng_f, engine_adj=eng_a, history="checkpoint K=%d" % seg if seg else "full")
