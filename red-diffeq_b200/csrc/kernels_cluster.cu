@@ -115,8 +115,10 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
 //              sweep runs it; level k of the loop is reverse time t = nt-1-k, the "source" is alpha * cotangent at the
 //              receiver cells, the history receives u_{nt-1} .. u_1 (slot k), and sum_t u_t[src] w_t is accumulated
 //              for the beta_dt term.  The imaging sums are formed afterwards by k_imaging from the two histories.
-template <int RMAX, int PITCH, bool ADJ>
-__global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdArgs a, Grid g)
+// NT = threads per CTA: 512 with one CTA per SM, or 256 with two CTAs (of two different clusters, i.e. two different
+// shots) per SM, so that one can issue while the other sits at its per-level barrier.
+template <int RMAX, int PITCH, bool ADJ, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFwdArgs a, Grid g)
 {
     extern __shared__ __align__(128) float smem[];
 
@@ -206,10 +208,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
     }
-    for (int i = tid; i <= g.nxp; i += kClusterThreads) s_rec_ptr[i] = a.rec_ptr[i];
-    for (int i = tid; i < g.nrec; i += kClusterThreads) s_rec_idx[i] = a.rec_idx[i];
+    for (int i = tid; i <= g.nxp; i += NT) s_rec_ptr[i] = a.rec_ptr[i];
+    for (int i = tid; i < g.nrec; i += NT) s_rec_idx[i] = a.rec_idx[i];
     if (wav_in_smem)
-        for (int i = tid; i < a.nt; i += kClusterThreads) s_wav[i] = a.wavelet[i];
+        for (int i = tid; i < a.nt; i += NT) s_wav[i] = a.wavelet[i];
     __syncthreads();
 
     int shot_iter = 0;
@@ -217,9 +219,9 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
         const int gshot = a.shot0 + shot;  // index into per-shot inputs/outputs other than the history of this launch
         const int b = gshot / g.ns, s = gshot - b * g.ns;
         // p_{-1} = p_{-2} = 0 (halo rows included); sponge tables of this model
-        for (int i = tid; i < 2 * slab; i += kClusterThreads) smem[i] = 0.0f;
+        for (int i = tid; i < 2 * slab; i += NT) smem[i] = 0.0f;
         const float *kap_b = a.kap + (size_t)b * (g.nbc + 1);
-        for (int i = tid; i < a.slabrows; i += kClusterThreads) {
+        for (int i = tid; i < a.slabrows; i += NT) {
             const int kz = sponge_index(r0 + i, g.nzp, g.nbc);
             smem[kap_off + i] = (i < nrows && kz >= 0) ? kap_b[kz] : 0.0f;
         }
@@ -347,7 +349,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
 bool cluster_config(const Plan &p, ClusterConfig *cfg)
 {
     const Grid &g = p.g;
-    const int groups_max = kClusterThreads / g.q4;
+    const int nthreads = p.cluster_threads == 256 ? 256 : kClusterThreads;
+    const int groups_max = nthreads / g.q4;
     if (groups_max < 1) return false;
     int max_smem = 0;
     if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device) != cudaSuccess) return false;
@@ -361,18 +364,21 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg)
         const int slabrows = ngroups * kClusterRowsMax;  // >= maxrows: rows past the slab are computed but never stored
         size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + g.nxp + 1 + g.nrec) * sizeof(float);
         if (smem > (size_t)max_smem) continue;
-        cfg->wav_smem = smem + (size_t)p.nt * sizeof(float) <= (size_t)max_smem;
+        const size_t room = nthreads == 256 ? (size_t)(113 * 1024) : (size_t)max_smem;  // two CTAs per SM must fit 228 KB
+        if (nthreads == 256 && smem > room) continue;
+        cfg->wav_smem = smem + (size_t)p.nt * sizeof(float) <= room;
         if (cfg->wav_smem) smem += (size_t)p.nt * sizeof(float);
+        cfg->nthreads = nthreads;
         cfg->C = C; cfg->maxrows = maxrows; cfg->ngroups = ngroups; cfg->slabrows = slabrows; cfg->smem = smem;
         return true;
     }
     return false;
 }
 
-template <int PITCH, bool ADJ>
+template <int PITCH, bool ADJ, int NT>
 static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
 {
-    auto kernel = k_fwd_cluster<kClusterRowsMax, PITCH, ADJ>;
+    auto kernel = k_fwd_cluster<kClusterRowsMax, PITCH, ADJ, NT>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
     if (e != cudaSuccess) return e;
     a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
@@ -386,7 +392,7 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cc.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(kClusterThreads);
+    cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = cc.smem;
     cfg.stream = st;
     // persistent: as many clusters as can be co-resident (or one per shot if fewer shots)
@@ -407,10 +413,14 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
 {
     const bool adj = a.adj_mode != 0;
+    if (cc.nthreads == 256) {  // two CTAs per SM (experimental; OpenFWI pitch and runtime pitch only)
+        if (p.g.pitch == 312) return adj ? launch_fwd_cluster_t<312, true, 256>(p, cc, a, st) : launch_fwd_cluster_t<312, false, 256>(p, cc, a, st);
+        return adj ? launch_fwd_cluster_t<0, true, 256>(p, cc, a, st) : launch_fwd_cluster_t<0, false, 256>(p, cc, a, st);
+    }
     switch (p.g.pitch) {  // production grids get immediate row offsets (OpenFWI 310+2, Marmousi/Overthrust 430+2)
-        case 312: return adj ? launch_fwd_cluster_t<312, true>(p, cc, a, st) : launch_fwd_cluster_t<312, false>(p, cc, a, st);
-        case 432: return adj ? launch_fwd_cluster_t<432, true>(p, cc, a, st) : launch_fwd_cluster_t<432, false>(p, cc, a, st);
-        default: return adj ? launch_fwd_cluster_t<0, true>(p, cc, a, st) : launch_fwd_cluster_t<0, false>(p, cc, a, st);
+        case 312: return adj ? launch_fwd_cluster_t<312, true, 512>(p, cc, a, st) : launch_fwd_cluster_t<312, false, 512>(p, cc, a, st);
+        case 432: return adj ? launch_fwd_cluster_t<432, true, 512>(p, cc, a, st) : launch_fwd_cluster_t<432, false, 512>(p, cc, a, st);
+        default: return adj ? launch_fwd_cluster_t<0, true, 512>(p, cc, a, st) : launch_fwd_cluster_t<0, false, 512>(p, cc, a, st);
     }
 }
 

@@ -316,6 +316,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "adj_mode") { if (value < 0 || value > 1) goto bad; p->adj_mode = (int)value; }
     else if (k == "timing") { clear_spans(p); p->timing = value != 0; }  // (re)starts the per-kernel-class timers
     else if (k == "u_chunk_shots") { if (value < 0) goto bad; p->u_chunk_shots = (int)value; }
+    else if (k == "cluster_threads") { if (value != 0 && value != 256 && value != 512) goto bad; p->cluster_threads = (int)value; }
     else if (k == "img_rows") { if (value < 0 || value > 3) goto bad; p->img_rows = (int)value; }
     else if (k == "cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->cluster_size = (int)value; }
     else if (k == "adj_cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->adj_cluster_size = (int)value; }

@@ -63,6 +63,7 @@ struct Plan {
     int cluster_size = 0;   // 0 = smallest cluster that fits
     int adj_cluster_size = 0;
     int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused k_adj_cluster
+    int cluster_threads = 0;  // 0/512 = one 512-thread CTA per SM; 256 = two 256-thread CTAs per SM (k_fwd_cluster)
     int last_split = 0;       // whether the last rdfwi_backward ran the split adjoint (reported by rdfwi_plan_get "adj_split")
     int img_rows = 0;         // imaging kernel variant: 0/3 = one row per thread, 3 CTAs/SM (default, measured best: 57 ms);
                               // 1 = one row, 4 CTAs/SM (63 ms); 2 = two rows per thread, 2 CTAs/SM (64 ms)
@@ -118,6 +119,7 @@ struct ClusterConfig {
     size_t smem = 0;  // dynamic shared memory per CTA
     int rmax = 0;     // rows per thread (template instantiation) of the adjoint kernel
     bool wav_smem = false;  // the wavelet is staged in shared memory
+    int nthreads = 512;     // threads per CTA
 };
 
 // Pointers of one step launch (forward).
