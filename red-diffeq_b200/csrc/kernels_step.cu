@@ -16,6 +16,8 @@
 // loops over the ns shots of its model, so alpha / kappa / T1 / T2 are fetched once and shared by the
 // shots.  Rows z-2..z+R+1 are loaded once as float4 and reused for the R rows (register z-marching);
 // x-neighbours outside the float4 are 4 scalar loads that hit L1.  grid = (float4 slots, models).
+#include <algorithm>
+
 #include "rdfwi_common.cuh"
 
 namespace rdfwi {
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(kThreads) k_fwd_step(FwdArgs a, Grid g)
     const float c2 = 4.0f / 3.0f;    // fp32(4.0/3.0), the reference's python scalar cast by the tensor op
     const float c3 = -1.0f / 12.0f;
 
-    for (int s = 0; s < g.ns; ++s) {
+    for (int s = blockIdx.z; s < g.ns; s += gridDim.z) {  // shots are dealt over grid.z when the grid would not fill the GPU
         const size_t shot = (size_t)(b * g.ns + s);
         const float *__restrict__ P1 = a.p1 + shot * a.ss_p1;
         const float *__restrict__ P0 = a.p0 + shot * a.ss_p0;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) k_adj_step(AdjArgs a, Grid g)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { ga[r][j] = 0.0f; gk[r][j] = 0.0f; }
 
-    for (int s = 0; s < g.ns; ++s) {
+    for (int s = blockIdx.z; s < g.ns; s += gridDim.z) {  // one imaging plane per (model, grid.z slice)
         const size_t so = (size_t)(b * g.ns + s) * g.level;
         const float *__restrict__ Q1 = a.q1 + so;
         const float *__restrict__ Q2 = a.q2 + so;
@@ -283,8 +285,8 @@ __global__ void __launch_bounds__(kThreads) k_adj_step(AdjArgs a, Grid g)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         if (z0 + r < g.nzp) {
-            float *pa = a.Ga + (size_t)b * g.level + roff[r + 2] + x;
-            float *pk = a.Gk + (size_t)b * g.level + roff[r + 2] + x;
+            float *pa = a.Ga + ((size_t)b * gridDim.z + blockIdx.z) * g.level + roff[r + 2] + x;
+            float *pk = a.Gk + ((size_t)b * gridDim.z + blockIdx.z) * g.level + roff[r + 2] + x;
             float4 va = ld4(pa), vk = ld4(pk);
             va.x += ga[r][0]; va.y += ga[r][1]; va.z += ga[r][2]; va.w += ga[r][3];
             vk.x += gk[r][0]; vk.y += gk[r][1]; vk.z += gk[r][2]; vk.w += gk[r][3];
@@ -296,12 +298,33 @@ __global__ void __launch_bounds__(kThreads) k_adj_step(AdjArgs a, Grid g)
 
 }  // namespace
 
+// grid.z slices over which the shots of a model are dealt so that a launch has at least ~2 waves of CTAs;
+// the adjoint keeps at least `min_per_slice` shots per slice (each slice owns an imaging plane: its read-modify-write
+// per level is amortised over the slice's shots)
+int shot_slices(const Plan &p, int blocks_xy, int nb, int min_per_slice)
+{
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+    const int want = (2 * 2 * sms + blocks_xy * nb - 1) / (blocks_xy * nb);  // 2 waves at ~2 CTAs per SM
+    int sz = std::min(want, std::max(1, p.g.ns / min_per_slice));
+    return std::max(1, std::min(sz, p.g.ns));
+}
+
+int adj_shot_slices(const Plan &p, int nb)
+{
+    const Grid &g = p.g;
+    const int R = p.adj_rows_per_thread;
+    const int groups = (g.nzp + R - 1) / R;
+    return shot_slices(p, (groups * g.q4 + kThreads - 1) / kThreads, nb, 4);
+}
+
 cudaError_t launch_fwd_step(const Plan &p, const FwdArgs &a, int nb, cudaStream_t st)
 {
     const Grid &g = p.g;
     const int R = p.rows_per_thread;
     const int groups = (g.nzp + R - 1) / R;
-    const dim3 grid((unsigned)((groups * g.q4 + kThreads - 1) / kThreads), (unsigned)nb);
+    const int bxy = (groups * g.q4 + kThreads - 1) / kThreads;
+    const dim3 grid((unsigned)bxy, (unsigned)nb, (unsigned)shot_slices(p, bxy, nb, 1));
     switch (R) {
         case 1: k_fwd_step<1><<<grid, kThreads, 0, st>>>(a, g); break;
         case 2: k_fwd_step<2><<<grid, kThreads, 0, st>>>(a, g); break;
@@ -316,7 +339,7 @@ cudaError_t launch_adj_step(const Plan &p, const AdjArgs &a, int nb, cudaStream_
     const Grid &g = p.g;
     const int R = p.adj_rows_per_thread;
     const int groups = (g.nzp + R - 1) / R;
-    const dim3 grid((unsigned)((groups * g.q4 + kThreads - 1) / kThreads), (unsigned)nb);
+    const dim3 grid((unsigned)((groups * g.q4 + kThreads - 1) / kThreads), (unsigned)nb, (unsigned)a.slices);
     switch (R) {
         case 1: k_adj_step<1><<<grid, kThreads, 0, st>>>(a, g); break;
         default: k_adj_step<2><<<grid, kThreads, 0, st>>>(a, g); break;

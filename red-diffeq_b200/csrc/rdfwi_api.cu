@@ -154,7 +154,8 @@ Workspace carve(const Plan &p, int B, void *base)
         w.u_chunk = (nshots + nchunks - 1) / nchunks;
         if (p.u_chunk_shots == 0 && w.u_chunk < nshots && w.u_chunk < 24 && fused_ok) { w.split = false; w.u_chunk = 0; }
     }
-    w.g_planes = (w.split || fused_ok) ? g.ns : 1;  // per-shot imaging planes
+    // imaging planes per model: one per shot for the cluster engines, one per grid.z slice for the per-level adjoint
+    w.g_planes = (w.split || fused_ok) ? g.ns : adj_shot_slices(p, w.nb);
     w.Ga = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gk = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gb = (float *)take((size_t)B * g.ns * 4);
@@ -317,6 +318,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "timing") { clear_spans(p); p->timing = value != 0; }  // (re)starts the per-kernel-class timers
     else if (k == "u_chunk_shots") { if (value < 0) goto bad; p->u_chunk_shots = (int)value; }
     else if (k == "cluster_threads") { if (value != 0 && value != 256 && value != 512) goto bad; p->cluster_threads = (int)value; }
+    else if (k == "img_prefetch") { if (value < 0 || value > 64) goto bad; p->img_prefetch = (int)value; }
     else if (k == "img_rows") { if (value < 0 || value > 3) goto bad; p->img_rows = (int)value; }
     else if (k == "cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->cluster_size = (int)value; }
     else if (k == "adj_cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->adj_cluster_size = (int)value; }
@@ -536,6 +538,9 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     const int nseg = ckpt ? num_segments(p, K) : 1;
     const size_t ck_stride = ckpt ? (size_t)(nseg - 1) * 2 * g.level : 0;
     Timed *timed_adj = new Timed(p, 3, st);
+    // per-level adjoint: shots dealt over grid.z slices, one imaging plane per slice (w.g_planes may be larger when a
+    // cluster configuration exists but the checkpointed path is taken; the planes actually used are pl_slices)
+    const int pl_slices = std::min(w.g_planes, adj_shot_slices(p, w.nb));
     RD_CUDA(cudaMemsetAsync(w.Ga, 0, (size_t)B * w.g_planes * g.level * sizeof(float), st));
     RD_CUDA(cudaMemsetAsync(w.Gk, 0, (size_t)B * w.g_planes * g.level * sizeof(float), st));
 
@@ -587,8 +592,9 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
                 a.cot = (t % p.st == 0) ? cot + (size_t)b0 * g.ns * g.nt_out * g.nrec : nullptr;
                 a.it_out = t / p.st;
                 a.w_t = p.wavelet[t];
-                a.Ga = w.Ga + (size_t)b0 * g.level;
-                a.Gk = w.Gk + (size_t)b0 * g.level;
+                a.slices = pl_slices;
+                a.Ga = w.Ga + (size_t)b0 * pl_slices * g.level;
+                a.Gk = w.Gk + (size_t)b0 * pl_slices * g.level;
                 a.Gb = w.Gb + (size_t)b0 * g.ns;
                 launch_adj_step(p, a, nb, st);
             }

@@ -64,6 +64,7 @@ struct Plan {
     int adj_cluster_size = 0;
     int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused k_adj_cluster
     int cluster_threads = 0;  // 0/512 = one 512-thread CTA per SM; 256 = two 256-thread CTAs per SM (k_fwd_cluster)
+    int img_prefetch = 0;     // imaging kernel: levels ahead pulled into L2 (0 = default 2)
     int last_split = 0;       // whether the last rdfwi_backward ran the split adjoint (reported by rdfwi_plan_get "adj_split")
     int img_rows = 0;         // imaging kernel variant: 0/3 = one row per thread, 3 CTAs/SM (default, measured best: 57 ms);
                               // 1 = one row, 4 CTAs/SM (63 ms); 2 = two rows per thread, 2 CTAs/SM (64 ms)
@@ -156,6 +157,7 @@ struct AdjArgs {
     float *Gk;  // (nb, nzp, pitch)  sum_t,s (q_{t+1}-q_t) p_{t-1}
     float *Gb;  // (nb, ns)          sum_t   q_t[src] w_t
     unsigned long long ss_pm1;  // floats between consecutive shots in pm1 (history or the zero level)
+    int slices;                 // grid.z slices the shots are dealt over = imaging planes per model (Ga, Gk)
 };
 
 void set_error(const std::string &msg);
@@ -167,6 +169,7 @@ cudaError_t launch_coefficients(const Plan &p, const float *v, int B, float *alp
 // kernels_step.cu
 cudaError_t launch_fwd_step(const Plan &p, const FwdArgs &a, int nb, cudaStream_t st);
 cudaError_t launch_adj_step(const Plan &p, const AdjArgs &a, int nb, cudaStream_t st);
+int adj_shot_slices(const Plan &p, int nb);  // imaging planes per model the per-level adjoint accumulates into
 // kernels_cluster.cu
 bool cluster_config(const Plan &p, ClusterConfig *cfg);
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st);
