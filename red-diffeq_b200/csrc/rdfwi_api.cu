@@ -311,7 +311,6 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     if (k == "chunk_models") { if (value < 0) goto bad; p->chunk_models = (int)value; }
     else if (k == "rows_per_thread") { if (value != 1 && value != 2 && value != 4) goto bad; p->rows_per_thread = (int)value; }
     else if (k == "adj_rows_per_thread") { if (value != 1 && value != 2) goto bad; p->adj_rows_per_thread = (int)value; }
-    else if (k == "use_graph") { p->use_graph = value != 0; }
     else if (k == "engine") { if (value < 0 || value > 2) goto bad; p->engine = (int)value; }
     else if (k == "history_segment") { if (value < 0 || value == 1 || value == 2) goto bad; p->history_segment = (int)value; }
     else if (k == "adj_mode") { if (value < 0 || value > 1) goto bad; p->adj_mode = (int)value; }
@@ -337,7 +336,6 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
     if (k == "chunk_models") *out = p->chunk_models;
     else if (k == "rows_per_thread") *out = p->rows_per_thread;
     else if (k == "adj_rows_per_thread") *out = p->adj_rows_per_thread;
-    else if (k == "use_graph") *out = p->use_graph;
     else if (k == "engine") *out = p->engine;
     else if (k == "history_segment") *out = p->history_segment;
     else if (k == "adj_mode") *out = p->adj_mode;

@@ -57,7 +57,6 @@ struct Plan {
     // options
     int chunk_models = 0;   // 0 = auto
     int rows_per_thread = 2;
-    int use_graph = 0;
     int adj_rows_per_thread = 1;
     int engine = 0;         // 0 = auto, 1 = per-level kernels, 2 = cluster-resident time loop
     int cluster_size = 0;   // 0 = smallest cluster that fits

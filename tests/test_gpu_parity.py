@@ -217,3 +217,62 @@ def test_errors():
     op = FWIForward(ctx, "cuda:0", normalize=False)
     with pytest.raises(IndexError):
         op(torch.tensor(g.v, device="cuda:0"))
+
+
+@pytest.mark.parametrize("nx,nbc", [(15, 9), (17, 9), (21, 10), (16, 8)])
+@pytest.mark.parametrize("engine", ["per-level", "cluster-split", "cluster-fused"])
+def test_odd_widths_against_oracle(nx, nbc, engine, oracle):
+    """Padded widths with nxp % 4 in {1, 3, 0, ...}: the periodic image columns of the pitched layout (1..3 of them)
+    must reproduce torch.roll's wrap-around bit for bit; no reference fixture has such a width, so the pinned oracle checks."""
+    from red_diffeq_b200 import FWIForward
+    ctx = dict(n_grid=nx, nt=125, dx=10.0, dt=0.001, nbc=nbc, f=25.0, sz=20, gz=10, ng=nx, ns=2)
+    nz = 11
+    rng = np.random.default_rng(nx * 100 + nbc)
+    v = (1500 + 3000 * rng.random((2, 1, nz, nx))).astype(np.float32)
+    op = FWIForward(dict(ctx), "cuda:0", normalize=False)
+    op.set_option("engine", 1 if engine == "per-level" else 2)
+    op.set_option("adj_mode", 1 if engine == "cluster-fused" else 0)
+    sv = oracle.Survey(dict(ctx), nz, nx)
+    cot = rng.standard_normal((2, sv.ns, sv.nt_out, sv.nrec)).astype(np.float32)
+    seis, grad = _run(op, v, cot)
+    seis_o, grad_o = oracle.gradient(sv, v, cot)
+    assert (sv.nxp % 4) == (nx + 2 * nbc) % 4
+    assert np.array_equal(seis, seis_o)
+    assert rel_l2(grad, grad_o) <= GRAD_TOL
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] at full size (64 OpenFWI models x 5 shots x 1000 levels, 124 GB of wavefield history):
+    size-independent properties -- every model of the batch is bit-identical to its solo run (seismograms and
+    gradient), and a repeated evaluation is bit-identical (no atomics anywhere)."""
+    from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize
+    from red_diffeq_b200.utils import synthetic
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150e9:
+        pytest.skip("needs ~130 GB of free HBM")
+    ctx = dict(synthetic.PDE_OPENFWI)
+    op = FWIForward(dict(ctx), "cuda:0", normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    B = 64
+    g = Golden("openfwi")
+    vn = synthetic.velocity_models(B, 70, 70)
+    vn[0] = g.v[0]                              # model 0 = the reference fixture's model
+    cot = synthetic.cotangent((B, 5, 1000, 70), seed=3)
+    v = torch.tensor(vn, device="cuda:0", requires_grad=True)
+    c = torch.tensor(cot, device="cuda:0")
+    seis = op(v)
+    seis.backward(c)
+    g1 = v.grad.clone()
+    v.grad = None
+    seis2 = op(v)
+    seis2.backward(c)
+    assert torch.equal(seis, seis2) and torch.equal(g1, v.grad)
+    assert np.array_equal(seis[:1].detach().cpu().numpy(), g.seis_f32)   # bit-identical to the reference inside a batch of 64
+    solo = FWIForward(dict(ctx), "cuda:0", normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    for b in (0, 31, 63):
+        vb = torch.tensor(vn[b:b + 1], device="cuda:0", requires_grad=True)
+        sb = solo(vb)
+        sb.backward(c[b:b + 1])
+        assert torch.equal(sb, seis[b:b + 1])
+        assert torch.equal(vb.grad, g1[b:b + 1])
+    op.release_memory()
+    solo.release_memory()
