@@ -256,22 +256,32 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
         cluster_sync_all();  // shot boundary: every CTA has finished the previous shot and cleared its buffers
 
         // one time level: p_{t-1} in buffer `cur`, p_{t-2} in `prv`, p_t overwrites p_{t-2}
+        // optional per-warp timeline (debug option "trace_ptr"): clock64 stamps of levels 100..103 of cluster 0's first shot
+        auto stamp = [&](const int t, const int phase) {
+            if (a.trace != nullptr && cid == 0 && shot_iter == 0 && t >= 100 && t < 104 && lane_id == 0)
+                a.trace[(((size_t)rank * 4 + (t - 100)) * (NT / 32) + (tid >> 5)) * 6 + phase] = clock64();
+        };
         auto level = [&](const int t, const int cur, const int prv) {
             const int cbuf = cur == 0 ? 0 : 1, pbuf = 1 - cbuf;
+            stamp(t, 0);
             uint64_t *bar_top = bars + 2 * cbuf, *bar_bot = bars + 2 * cbuf + 1;
             const bool sends = t + 1 < a.nt;  // the last level of a shot has no consumer
+            // Arm the barriers of the buffer written NOW (consumed at level t+1) before the neighbours' rows can land: a
+            // waiter that finds its phase already complete returns at once, whereas arming at the consumer's level start
+            // raced with the waiters and cost them a ~3600-cycle try_wait time-out per level (tools/trace_levels.py).
+            if (tid == 0 && sends) {
+                mbar_expect_tx(bars + 2 * pbuf, halo_bytes);
+                mbar_expect_tx(bars + 2 * pbuf + 1, halo_bytes);
+            }
             if (t >= 1) {
                 // the halos of `cur` were sent by the neighbours early in level t-1 (t = 0: zero initial state)
                 const uint32_t parity = (uint32_t)((shot_iter * (cbuf ? uses1 : uses0) + (t - 1) / 2) & 1);
-                if (tid == 0) {
-                    mbar_expect_tx(bar_top, halo_bytes);
-                    mbar_expect_tx(bar_bot, halo_bytes);
-                }
                 if (warp_active) {
                     if (rd_top) mbar_wait(bar_top, parity);
                     if (rd_bot) mbar_wait(bar_bot, parity);
                 }
             }
+            stamp(t, 1);
             const int p0 = prv + 2 * pitch + th.x;
             const int trev = a.nt - 1 - t;  // adjoint mode: the reverse-time level this iteration computes
             float cot4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -285,6 +295,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
                 const uint64_t *push_bar = bars + 2 * pbuf + hp.bar;  // barrier of the buffer written now, at the receiver
                 if (rev) fwd_sweep<RMAX, PITCH, -1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
                 else fwd_sweep<RMAX, PITCH, 1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
+                stamp(t, 2);
                 if (ADJ) {
                     if (th.rec_lr >= 0 && trev % a.st == 0) {  // u_t[rec] += alpha * g_t  (adjoint of the gather, :83)
                         float4 v = ld4(smem + p0 + th.rec_lr * pitch);
@@ -304,14 +315,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
                     if (src_mask & 8) v.w = __fadd_rn(v.w, src_add);
                     st4(smem + p0 + th.src_lr * pitch, v);
                 }
-                if (!ADJ && th.rec_lr >= 0 && t % a.st == 0) {  // sampled after injection (solvers/pde.py:82-83)
-                    float *seis_t = a.seis + ((size_t)gshot * g.nt_out + t / a.st) * g.nrec;
-                    const float4 v = ld4(smem + p0 + th.rec_lr * pitch);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (th.x + j < g.nxp)
-                            for (int k = s_rec_ptr[th.x + j]; k < s_rec_ptr[th.x + j + 1]; ++k) seis_t[s_rec_idx[k]] = lane(v, j);
-                }
                 if (late != 0 && sends) {  // edge rows that could not leave from inside the sweep
                     for (int h = 0; h < 2; ++h) {
                         if (late & (1 << h))
@@ -323,11 +326,24 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
                     }
                 }
             }
+            stamp(t, 3);
             if (a.hist != nullptr) {
                 fence_proxy_async();             // slab writes -> visible to the bulk-copy engine
                 if (tid == 0) bulk_wait_read();  // the copy of the previous level has finished reading its buffer
             }
+            stamp(t, 4);
             __syncthreads();                     // rows of level t are complete CTA-wide
+            stamp(t, 5);
+            // Receiver sampling (solvers/pde.py:82-83, after the source injection) is done by the CTA's last warp -- which
+            // usually owns no rows -- from the finished level while the other warps already sweep the next one (that
+            // buffer is read-only until the barrier after next).  In the owner threads' epilogue it sat on the critical
+            // path of the whole cluster: ~1900 of 9000 cycles per level (tools/trace_levels.py).
+            if (!ADJ && tid >= NT - 32 && t % a.st == 0 && g.igz >= r0 && g.igz < r0 + nrows) {
+                float *seis_t = a.seis + ((size_t)gshot * g.nt_out + t / a.st) * g.nrec;
+                const float *row = smem + prv + (2 + g.igz - r0) * pitch;
+                for (int xx = lane_id; xx < g.nxp; xx += 32)
+                    for (int k = s_rec_ptr[xx]; k < s_rec_ptr[xx + 1]; ++k) seis_t[s_rec_idx[k]] = row[xx];
+            }
             if (a.hist != nullptr && tid == 0 && t <= a.nt - 2)
                 bulk_store(a.hist + (size_t)shot * hist_shot + (size_t)t * g.level + (size_t)r0 * pitch,
                            smem + prv + 2 * pitch, (uint32_t)(nrows * pitch * sizeof(float)));

@@ -288,12 +288,12 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_adj_cluster(ClusterAdjAr
             const int cbuf = cur == 0 ? 0 : 1, pbuf = 1 - cbuf;
             uint64_t *bar_top = bars + 2 * cbuf, *bar_bot = bars + 2 * cbuf + 1;
             const bool sends = t > 0;  // u_0 has no consumer
+            if (tid == 0 && sends) {   // arm the barriers of the buffer written now, before the neighbours' rows can land
+                mbar_expect_tx(bars + 2 * pbuf, halo_bytes);
+                mbar_expect_tx(bars + 2 * pbuf + 1, halo_bytes);
+            }
             if (k >= 1) {
                 const uint32_t parity = (uint32_t)((shot_iter * (cbuf ? uses1 : uses0) + (k - 1) / 2) & 1);
-                if (tid == 0) {
-                    mbar_expect_tx(bar_top, halo_bytes);
-                    mbar_expect_tx(bar_bot, halo_bytes);
-                }
                 if (warp_active) {
                     if (rd_top) mbar_wait(bar_top, parity);
                     if (rd_bot) mbar_wait(bar_bot, parity);

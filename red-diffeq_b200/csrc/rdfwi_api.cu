@@ -318,6 +318,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "u_chunk_shots") { if (value < 0) goto bad; p->u_chunk_shots = (int)value; }
     else if (k == "cluster_threads") { if (value != 0 && value != 256 && value != 512) goto bad; p->cluster_threads = (int)value; }
     else if (k == "img_prefetch") { if (value < 0 || value > 64) goto bad; p->img_prefetch = (int)value; }
+    else if (k == "trace_ptr") { p->trace_ptr = reinterpret_cast<long long *>(value); }
     else if (k == "img_rows") { if (value < 0 || value > 3) goto bad; p->img_rows = (int)value; }
     else if (k == "cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->cluster_size = (int)value; }
     else if (k == "adj_cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->adj_cluster_size = (int)value; }
@@ -414,7 +415,7 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
         ClusterFwdArgs a{};
         a.alpha = w.alpha; a.kap = w.kap; a.beta_src = w.beta_src;
         a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx; a.wavelet = p.d_wavelet;
-        a.seis = seis; a.hist = hist;
+        a.seis = seis; a.hist = hist; a.trace = p.trace_ptr;
         a.nshots = B * g.ns; a.nt = nt; a.st = p.st;
         Timed timed(p, 0, st);
         RD_CUDA(launch_fwd_cluster(p, cc, a, st));

@@ -64,6 +64,7 @@ struct Plan {
     int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused k_adj_cluster
     int cluster_threads = 0;  // 0/512 = one 512-thread CTA per SM; 256 = two 256-thread CTAs per SM (k_fwd_cluster)
     int img_prefetch = 0;     // imaging kernel: levels ahead pulled into L2 (0 = default 2)
+    long long *trace_ptr = nullptr;  // debug: device buffer for per-warp timeline stamps of k_fwd_cluster
     int last_split = 0;       // whether the last rdfwi_backward ran the split adjoint (reported by rdfwi_plan_get "adj_split")
     int img_rows = 0;         // imaging kernel variant: 0/3 = one row per thread, 3 CTAs/SM (default, measured best: 57 ms);
                               // 1 = one row, 4 CTAs/SM (63 ms); 2 = two rows per thread, 2 CTAs/SM (64 ms)
@@ -87,6 +88,7 @@ struct ClusterFwdArgs {
     float *seis;            // (B*ns, nt_out, nrec)
     float *hist;            // [shot][t][z][x], t = 0..nt-2, or nullptr (indexed by the launch-local shot)
     int nshots, nt, st;
+    long long *trace;       // debug: per-warp clock64 stamps (nullptr = off)
     int shot0;              // global index of the launch's first shot (seis / cot / Gb / model lookup)
     int adj_mode;           // 0 = forward wavefield, 1 = adjoint field in the u-variable (see k_fwd_cluster)
     const float *cot;       // adjoint mode: (B*ns, nt_out, nrec) cotangent of the seismograms
