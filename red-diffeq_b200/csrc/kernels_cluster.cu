@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
     // receiver CSR (columns -> receiver slots) and, when it fits, the wavelet
     int *s_rec_ptr = reinterpret_cast<int *>(bars + 4);
     int *s_rec_idx = s_rec_ptr + g.nxp + 1;
-    float *s_wav = reinterpret_cast<float *>(s_rec_idx + g.nrec);
+    float *s_cot = reinterpret_cast<float *>(s_rec_idx + g.nrec);  // [2][nxp] per-column cotangent sums (adjoint mode)
+    float *s_wav = s_cot + 2 * g.nxp;
     const bool wav_in_smem = a.wav_smem != 0;
 
     const int tid = threadIdx.x, lane_id = tid & 31;
@@ -252,6 +253,18 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
             for (int j = 0; j < 4; ++j)
                 if (th.src_lr >= 0 && th.x + j < g.nxp && th.x + j == xs) src_lane = j;
         }
+        const bool has_rec_row = g.igz >= r0 && g.igz < r0 + nrows;
+        auto stage_cot = [&](const int tr, const int buf) {  // executed by one warp
+            float *dst = s_cot + buf * g.nxp;
+            if (tr % a.st != 0) return;
+            const float *gt = a.cot + ((size_t)gshot * g.nt_out + tr / a.st) * g.nrec;
+            for (int xx = lane_id; xx < g.nxp; xx += 32) {
+                float acc = 0.0f;
+                for (int k = s_rec_ptr[xx]; k < s_rec_ptr[xx + 1]; ++k) acc += gt[s_rec_idx[k]];
+                dst[xx] = acc;
+            }
+        };
+        if (ADJ && tid >= NT - 32 && has_rec_row) stage_cot(a.nt - 1, 0);  // level 0 of the loop is reverse time nt-1
         __syncthreads();
         cluster_sync_all();  // shot boundary: every CTA has finished the previous shot and cleared its buffers
 
@@ -284,13 +297,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
             stamp(t, 1);
             const int p0 = prv + 2 * pitch + th.x;
             const int trev = a.nt - 1 - t;  // adjoint mode: the reverse-time level this iteration computes
-            float cot4[4] = {0.f, 0.f, 0.f, 0.f};
-            if (ADJ && th.rec_lr >= 0 && trev % a.st == 0) {  // fetched before the sweep, consumed after it
-                const float *gt = a.cot + ((size_t)gshot * g.nt_out + trev / a.st) * g.nrec;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    for (int k = s_rec_ptr[xc[j]]; k < s_rec_ptr[xc[j] + 1]; ++k) cot4[j] += gt[s_rec_idx[k]];
-            }
+            // The cotangent of the NEXT reverse level is staged (summed per column) in shared memory by the CTA's last
+            // warp while the others sweep: fetched by the owner threads themselves, the dependent global loads stalled
+            // their in-order sweep by ~2500 cycles per level on the cluster's critical path (tools/trace_levels.py).
+            if (ADJ && tid >= NT - 32 && has_rec_row && t + 1 < a.nt) stage_cot(trev - 1, (t + 1) & 1);
             if (warp_active) {
                 const uint64_t *push_bar = bars + 2 * pbuf + hp.bar;  // barrier of the buffer written now, at the receiver
                 if (rev) fwd_sweep<RMAX, PITCH, -1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
@@ -299,7 +309,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
                 if (ADJ) {
                     if (th.rec_lr >= 0 && trev % a.st == 0) {  // u_t[rec] += alpha * g_t  (adjoint of the gather, :83)
                         float4 v = ld4(smem + p0 + th.rec_lr * pitch);
-                        v.x += al_rec.x * cot4[0]; v.y += al_rec.y * cot4[1]; v.z += al_rec.z * cot4[2]; v.w += al_rec.w * cot4[3];
+                        const float *cc = s_cot + (t & 1) * g.nxp;
+                        v.x += al_rec.x * cc[xc[0]]; v.y += al_rec.y * cc[xc[1]]; v.z += al_rec.z * cc[xc[2]]; v.w += al_rec.w * cc[xc[3]];
                         st4(smem + p0 + th.rec_lr * pitch, v);
                     }
                     if (src_lane >= 0) {  // adjoint of the source injection (:81)
@@ -378,7 +389,7 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg)
         const int ngroups = (maxrows + kClusterRowsMax - 1) / kClusterRowsMax;  // each thread marches kClusterRowsMax rows
         if (ngroups > groups_max) continue;
         const int slabrows = ngroups * kClusterRowsMax;  // >= maxrows: rows past the slab are computed but never stored
-        size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + g.nxp + 1 + g.nrec) * sizeof(float);
+        size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + g.nxp + 1 + g.nrec + 2 * g.nxp) * sizeof(float);
         if (smem > (size_t)max_smem) continue;
         const size_t room = nthreads == 256 ? (size_t)(113 * 1024) : (size_t)max_smem;  // two CTAs per SM must fit 228 KB
         if (nthreads == 256 && smem > room) continue;

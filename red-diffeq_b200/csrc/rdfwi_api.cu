@@ -507,7 +507,7 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
             a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx; a.wavelet = p.d_wavelet;
             a.seis = nullptr; a.hist = w.u_hist;
             a.nshots = n; a.nt = nt; a.st = p.st;
-            a.shot0 = s0; a.adj_mode = 1; a.cot = cot; a.Gb = w.Gb;
+            a.shot0 = s0; a.adj_mode = 1; a.cot = cot; a.Gb = w.Gb; a.trace = p.trace_ptr;
             {
                 Timed timed(p, 1, st);
                 RD_CUDA(launch_fwd_cluster(p, cc, a, st));
