@@ -341,12 +341,12 @@ def main():
         }
         if adj_split:
             # the adjoint's 16 B / cell-update split as: adjoint-field kernel (read u_{t+1}, u_{t+2}, write u_t = 12 B; all of
-            # it stays in shared memory, only the 4 B history write reaches HBM) + imaging kernel (read p_{t-1}, u_t = 8 B,
-            # of which u_t is traffic the fused formulation would not have: counted, it is what the kernel really streams)
+            # it stays in shared memory, only the 4 B history write reaches HBM) + imaging kernel (pointwise: read p_t and
+            # u_t once each = 8 B, which is exactly what it streams from HBM)
             kernels["adjoint_field"] = {"kernel": "k_fwd_cluster<ADJ>", "us": us["adjoint_field"], "launches": n["adjoint_field"],
                                         "algo_bytes": 12.0 * cell_updates}
             kernels["imaging"] = {"kernel": "k_imaging", "us": us["imaging"], "launches": n["imaging"],
-                                  "algo_bytes": 8.0 * float(cells_level) * (nt - 1)}
+                                  "algo_bytes": 8.0 * cell_updates}
         else:
             kernels["adjoint_loop"] = {"kernel": "k_adj_cluster" if adj_cluster else "k_adj_step", "us": us["adjoint_loop"],
                                        "launches": n["adjoint_loop"] if adj_cluster else launches_b - 7,

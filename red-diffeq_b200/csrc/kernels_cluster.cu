@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
         if (rb >= th.la && rb < th.lb && !(hp.early && hp.bar == 0)) late |= 4 << h;
     }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t hist_shot = (size_t)(a.nt - 1) * g.level;
+    const size_t hist_shot = (size_t)a.nt * g.level;  // the history keeps every level
     const uint32_t halo_bytes = (uint32_t)(2 * pitch * sizeof(float));
     // halo phases consumed per shot from buffer 1 (levels 1,3,..) and buffer 0 (levels 2,4,..)
     const int uses1 = a.nt / 2, uses0 = (a.nt - 1) / 2;
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
                 for (int xx = lane_id; xx < g.nxp; xx += 32)
                     for (int k = s_rec_ptr[xx]; k < s_rec_ptr[xx + 1]; ++k) seis_t[s_rec_idx[k]] = row[xx];
             }
-            if (a.hist != nullptr && tid == 0 && t <= a.nt - 2)
+            if (a.hist != nullptr && tid == 0)
                 bulk_store(a.hist + (size_t)shot * hist_shot + (size_t)t * g.level + (size_t)r0 * pitch,
                            smem + prv + 2 * pitch, (uint32_t)(nrows * pitch * sizeof(float)));
         };

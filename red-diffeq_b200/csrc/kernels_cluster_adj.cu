@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_adj_cluster(ClusterAdjAr
         if (rb >= th.la && rb < th.lb && !(hp.early && hp.bar == 0)) late |= 4 << h;
     }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t hist_shot = (size_t)(a.nt - 1) * g.level;
+    const size_t hist_shot = (size_t)a.nt * g.level;  // the history keeps every level (the last one is not read here)
     const uint32_t halo_bytes = (uint32_t)(2 * pitch * sizeof(float));
     // u-halo phases consumed per shot: reverse level index k = nt-1-t; buffer roles alternate with k
     const int uses1 = a.nt / 2, uses0 = (a.nt - 1) / 2;

@@ -147,7 +147,7 @@ Workspace carve(const Plan &p, int B, void *base)
         // shots whose adjoint-field history is in flight at once: two waves of 33 four-CTA clusters, evened out over the
         // chunks, and at most ~40 GB of scratch; long records that leave less than a wave per chunk use the fused kernel
         const int nshots = B * g.ns;
-        const double per_shot = (double)std::max(p.nt - 1, 1) * (double)g.level * sizeof(float);
+        const double per_shot = (double)p.nt * (double)g.level * sizeof(float);
         int chunk = p.u_chunk_shots > 0 ? p.u_chunk_shots : std::min(66, std::max(1, (int)(40e9 / per_shot)));
         chunk = std::min(chunk, nshots);
         const int nchunks = (nshots + chunk - 1) / chunk;
@@ -164,7 +164,7 @@ Workspace carve(const Plan &p, int B, void *base)
     // checkpoint mode: the levels of one segment of one chunk, recomputed during the backward pass
     w.seg_hist = p.history_segment > 0 ? (float *)take(w.chunk_level * (size_t)(p.history_segment - 1) * 4) : nullptr;
     // split adjoint: adjoint-field history of one chunk of shots
-    if (w.split) w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)std::max(p.nt - 1, 1) * g.level * 4);
+    if (w.split) w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
     w.bytes = off;
     return w;
 }
@@ -190,7 +190,7 @@ size_t history_floats(const Plan &p, int B, int segment)
 {
     if (segment > 0)  // the pair (p_{jK-2}, p_{jK-1}) in front of every segment j >= 1
         return (size_t)B * p.g.ns * (size_t)std::max(num_segments(p, segment) - 1, 0) * 2 * p.g.level;
-    return (size_t)B * p.g.ns * (size_t)std::max(p.nt - 1, 0) * p.g.level;
+    return (size_t)B * p.g.ns * (size_t)p.nt * p.g.level;  // every level p_0 .. p_{nt-1}
 }
 
 int check_segment(const Plan &p, int segment)
@@ -319,7 +319,6 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "cluster_threads") { if (value != 0 && value != 256 && value != 512) goto bad; p->cluster_threads = (int)value; }
     else if (k == "img_prefetch") { if (value < 0 || value > 64) goto bad; p->img_prefetch = (int)value; }
     else if (k == "trace_ptr") { p->trace_ptr = reinterpret_cast<long long *>(value); }
-    else if (k == "img_rows") { if (value < 0 || value > 3) goto bad; p->img_rows = (int)value; }
     else if (k == "cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->cluster_size = (int)value; }
     else if (k == "adj_cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->adj_cluster_size = (int)value; }
     else { set_error("unknown option " + k); return RDFWI_EINVAL; }
@@ -430,7 +429,7 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
     for (int b0 = 0; b0 < B; b0 += w.nb) {
         const int nb = std::min(w.nb, B - b0);
         const size_t lvl = (size_t)nb * g.ns * g.level;  // floats per level of this chunk
-        const size_t hstride = (size_t)(nt - 1) * g.level;  // shot stride inside the history
+        const size_t hstride = (size_t)nt * g.level;  // shot stride inside the history
         float *hbase = hist ? hist + (size_t)b0 * g.ns * hstride : nullptr;
         if (!hist || ckpt) RD_CUDA(cudaMemsetAsync(w.fields, 0, 3 * w.chunk_level * sizeof(float), st));
         (void)lvl;
@@ -450,8 +449,8 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
             }
             if (hist) {
                 if (t < 0) return w.zero;
-                if (t <= nt - 2) { *stride = hstride; return hbase + (size_t)t * g.level; }
-                return w.fields;
+                *stride = hstride;
+                return hbase + (size_t)t * g.level;
             }
             return w.fields + (size_t)((t + 3) % 3) * w.chunk_level;
         };
@@ -513,7 +512,7 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
                 RD_CUDA(launch_fwd_cluster(p, cc, a, st));
             }
             Timed timed(p, 2, st);
-            RD_CUDA(launch_imaging(p, hist, w.u_hist, w.alpha, w.Ga, w.Gk, s0, n, st));
+            RD_CUDA(launch_imaging(p, hist, w.u_hist, w.alpha, w.kap, w.beta_src, w.Gb, w.Ga, w.Gk, s0, n, st));
         }
         RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
         return RDFWI_OK;
@@ -546,7 +545,7 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     for (int b0 = 0; b0 < B; b0 += w.nb) {
         const int nb = std::min(w.nb, B - b0);
         const size_t lvl = (size_t)nb * g.ns * g.level;
-        const size_t hstride = (size_t)(nt - 1) * g.level;
+        const size_t hstride = (size_t)nt * g.level;
         const float *hbase = hist + (size_t)b0 * g.ns * hstride;
         (void)lvl;
         RD_CUDA(cudaMemsetAsync(w.fields, 0, 3 * w.chunk_level * sizeof(float), st));  // q_{nt} = q_{nt+1} = 0

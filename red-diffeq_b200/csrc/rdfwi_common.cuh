@@ -63,11 +63,9 @@ struct Plan {
     int adj_cluster_size = 0;
     int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused k_adj_cluster
     int cluster_threads = 0;  // 0/512 = one 512-thread CTA per SM; 256 = two 256-thread CTAs per SM (k_fwd_cluster)
-    int img_prefetch = 0;     // imaging kernel: levels ahead pulled into L2 (0 = default 2)
+    int img_prefetch = 0;     // imaging kernel: levels ahead pulled into L2 (0 = default 4)
     long long *trace_ptr = nullptr;  // debug: device buffer for per-warp timeline stamps of k_fwd_cluster
     int last_split = 0;       // whether the last rdfwi_backward ran the split adjoint (reported by rdfwi_plan_get "adj_split")
-    int img_rows = 0;         // imaging kernel variant: 0/3 = one row per thread, 3 CTAs/SM (default, measured best: 57 ms);
-                              // 1 = one row, 4 CTAs/SM (63 ms); 2 = two rows per thread, 2 CTAs/SM (64 ms)
     int u_chunk_shots = 0;    // shots whose adjoint-field history is in flight at once in split mode (0 = auto)
     // optional per-kernel-class timing with CUDA events on the caller's stream (rdfwi_plan_set "timing")
     int timing = 0;
@@ -178,8 +176,8 @@ cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFw
 bool adj_cluster_config(const Plan &p, ClusterConfig *cfg);
 cudaError_t launch_adj_cluster(const Plan &p, const ClusterConfig &cc, ClusterAdjArgs a, cudaStream_t st);
 // kernels_imaging.cu: zero-lag imaging sums of `nshots` shots from the forward history and the adjoint-field history
-cudaError_t launch_imaging(const Plan &p, const float *phist, const float *uhist, const float *alpha, float *Ga, float *Gk,
-                           int shot0, int nshots, cudaStream_t st);
+cudaError_t launch_imaging(const Plan &p, const float *phist, const float *uhist, const float *alpha, const float *kap,
+                           const float *beta_src, const float *Gb, float *Ga, float *Gk, int shot0, int nshots, cudaStream_t st);
 // kernels_epilogue.cu  (planes = imaging planes per model: 1 for the per-level engine, ns for the cluster engine)
 cudaError_t launch_gradient_epilogue(const Plan &p, const float *v, int B, const float *Ga, const float *Gk,
                                      const float *Gb, int planes, const int *argmin, float *fold_tmp,
