@@ -52,7 +52,7 @@ NCU_TRAFFIC_BYTES = {
     # 64-shot u history; each imaging launch reads both histories of its 64 shots
     ("openfwi_b64", "forward"): 123.8e9,
     ("openfwi_b64", "adjoint_field"): 24.7e9,
-    ("openfwi_b64", "imaging"): 53.1e9,
+    ("openfwi_b64", "imaging"): 52.2e9,      # profiles/ncu_imaging_r1_final_b64.txt (--set full): 52.11 GB read + 0.05 GB written
     # fused cluster adjoint (adj_mode=1), profiles/ncu_adj_cluster_r1_full_b64.txt
     ("openfwi_b64", "adjoint_loop"): 124.13e9,
 }

@@ -80,7 +80,7 @@ size_t rdfwi_level_floats(rdfwi_plan plan);
 size_t rdfwi_workspace_bytes(rdfwi_plan plan, int32_t B);
 
 /* Bytes of wavefield history rdfwi_forward must be given so that rdfwi_backward can run.
- *   segment == 0 : every level is kept (B*ns*(nt-1) levels)
+ *   segment == 0 : every level is kept (B*ns*nt levels)
  *   segment == K : the pair (p_{jK-2}, p_{jK-1}) in front of every segment j >= 1 of K levels is kept; the backward
  *                  pass recomputes one segment at a time into the workspace (one extra forward, memory / (K/2)).
  *                  May be 0 bytes (single segment): a NULL history is then accepted by rdfwi_backward. */

@@ -9,7 +9,7 @@
 //   reference's torch.roll wrap-around (solvers/pde.py:79) is honoured without a branch in the
 //   stencil; only the four scalar x-neighbour loads and the row offsets use wrapped indices.
 //   Rotating scratch levels are stored level(t)[shot][z][x]; the wavefield history is shot-major,
-//   hist[shot][t][z][x] for t = 0 .. nt-2, so one shot's levels stream contiguously (the cluster-resident
+//   hist[shot][t][z][x] for t = 0 .. nt-1, so one shot's levels stream contiguously (the cluster-resident
 //   kernels write / read them with 1-D bulk copies) and the per-level kernels address it with a shot stride.
 #pragma once
 
