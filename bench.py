@@ -36,9 +36,10 @@ WORKLOADS = {
     "openfwi_b1": ("openfwi", 70, 70, 1),         # configs[0]
     "marmousi_b1": ("marmousi", 70, 190, 1),      # configs[2] shape, reference shot count (5)
     "marmousi_b16": ("marmousi", 70, 190, 16),
-    # configs[2]: ONE Marmousi-shaped model, 40 shots (the reference's 5 do not divide over 8 GPUs)
-    # sharded over the ranks by ShardedFWIForward: strong scaling, one gradient all-reduce per step
-    "marmousi_sharded": ("marmousi40", 70, 190, 1),
+    # configs[2]: ONE Marmousi-shaped model, 192 shots (the reference's 5 do not divide over 8 GPUs; 192 =
+    # 8 GPUs x one wave of 24 six-CTA clusters) sharded over the ranks by ShardedFWIForward: strong scaling, one
+    # gradient all-reduce per step
+    "marmousi_sharded": ("marmousi192", 70, 190, 1),
     # configs[3]: Overthrust shape (= the Marmousi grid in the reference's configs) with a long record, nt = 4000
     # (synthetic extension); run with --history-segment K to exercise wavefield checkpointing
     "overthrust_long": ("overthrust4000", 70, 190, 8),
@@ -63,8 +64,8 @@ def make_ctx(kind):
     if kind == "openfwi":
         return dict(synthetic.PDE_OPENFWI)
     ctx = dict(synthetic.PDE_MARMOUSI)
-    if kind == "marmousi40":
-        ctx["ns"] = 40
+    if kind == "marmousi192":
+        ctx["ns"] = 192
     if kind == "overthrust4000":
         ctx["nt"] = 4000
     return ctx
@@ -219,7 +220,7 @@ def main():
     ns, nt, nbc = ctx["ns"], ctx["nt"], ctx["nbc"]
     nzp, nxp = nz + 2 * nbc, nx + 2 * nbc
     if sharded:
-        # strong scaling: the same 1 x 40 shots whatever the rank count; every rank models its shots
+        # strong scaling: the same 1 x 192 shots whatever the rank count; every rank models its shots
         wrapper = ShardedFWIForward(dict(ctx), dev, mode="shots", normalize=True, v_denorm_func=v_denormalize,
                                     s_norm_func=s_normalize_none)
         _, _, my_shots = wrapper.partition(B)
@@ -329,15 +330,19 @@ def main():
         # each class of launches inside the timed region (rdfwi_plan_set "timing").
         plan = op._plan_for(nz, nx, dev)
         eng = op.options.get("engine", 0)
-        fwd_cluster = eng != 1 and plan.get("cluster_size_used") > 0 and plan.get("history_segment") == 0
-        adj_split = plan.get("adj_split") == 1
-        adj_cluster = (not adj_split) and eng != 1 and plan.get("adj_cluster_size_used") > 0 and plan.get("history_segment") == 0
+        seg = plan.get("history_segment")
+        recompute = plan.get("adj_split") == 2      # no history kept: the backward pass re-runs the forward kernel per chunk
+        fwd_cluster = eng != 1 and plan.get("cluster_size_used") > 0 and (seg == 0 or recompute)
+        adj_split = plan.get("adj_split") >= 1
+        adj_cluster = (not adj_split) and eng != 1 and plan.get("adj_cluster_size_used") > 0 and seg == 0
         us = {k: kernel_us[k] / args.steps for k in kernel_us}
         n = {k: kernel_n[k] // args.steps for k in kernel_n}
         cell_updates = float(cells_level) * nt
         kernels = {
             "forward": {"kernel": "k_fwd_cluster<EXACT>" if fwd_cluster else "k_fwd_step", "us": us["forward"],
-                        "launches": n["forward"] if fwd_cluster else launches_f - 3, "algo_bytes": ALGO_BYTES_FWD * cell_updates},
+                        "launches": n["forward"] if fwd_cluster else launches_f - 3,
+                        # recompute tier: the forward kernel really runs twice per step (modelling + per-chunk recompute)
+                        "algo_bytes": ALGO_BYTES_FWD * cell_updates * (2 if recompute else 1)},
         }
         if adj_split:
             # the adjoint's 16 B / cell-update split as: adjoint-field kernel (read u_{t+1}, u_{t+2}, write u_t = 12 B; all of
@@ -368,9 +373,10 @@ def main():
             "config": {"workload": args.workload, "models_per_gpu": B, "shots_per_model": ns,
                        "shots_on_rank0": ns_local, "nt": nt,
                        "padded_grid": [nzp, nxp], "pairs_per_step_per_gpu": pairs_rank,
-                       "l2_policy": "working set (wavefield history %.1f GB) far exceeds the 126 MB L2; no flush needed"
-                                    % (op._plan_for(nz, nx, dev).history_bytes(B, op._plan_for(nz, nx, dev).get("history_segment")) / 1e9),
-                       "history": ("checkpoint pairs every %d levels" % plan.get("history_segment")) if plan.get("history_segment") else "every level",
+                       "l2_policy": "working set (wavefield histories, %.1f GB streamed per step) far exceeds the 126 MB L2; no flush needed"
+                                    % ((plan.history_bytes(B, seg) + plan.workspace_bytes(B)) / 1e9),
+                       "history": ("none kept: forward field recomputed per chunk of %d shots in the backward pass" % plan.get("u_chunk_used")) if recompute
+                                  else (("checkpoint pairs every %d levels" % seg) if seg else "every level"),
                        "engine": {"forward": "cluster-resident (C=%d)" % plan.get("cluster_size_used") if fwd_cluster else "per-level",
                                   "adjoint": ("split: cluster-resident adjoint field (C=%d) + streaming imaging" % plan.get("cluster_size_used")) if adj_split
                                   else ("cluster-resident fused (C=%d)" % plan.get("adj_cluster_size_used") if adj_cluster else "per-level")},

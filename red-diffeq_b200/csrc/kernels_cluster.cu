@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
     int *s_rec_ptr = reinterpret_cast<int *>(bars + 4);
     int *s_rec_idx = s_rec_ptr + g.nxp + 1;
     float *s_cot = reinterpret_cast<float *>(s_rec_idx + g.nrec);  // [2][nxp] per-column cotangent sums (adjoint mode)
-    float *s_wav = s_cot + 2 * g.nxp;
+    float *s_raw = s_cot + 2 * g.nxp;  // [2][nrec] cotangent rows as they sit in HBM, landed by cp.async (adjoint mode)
+    float *s_wav = s_raw + 2 * g.nrec;
     const bool wav_in_smem = a.wav_smem != 0;
 
     const int tid = threadIdx.x, lane_id = tid & 31;
@@ -254,17 +255,36 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
                 if (th.src_lr >= 0 && th.x + j < g.nxp && th.x + j == xs) src_lane = j;
         }
         const bool has_rec_row = g.igz >= r0 && g.igz < r0 + nrows;
-        auto stage_cot = [&](const int tr, const int buf) {  // executed by one warp
-            float *dst = s_cot + buf * g.nxp;
-            if (tr % a.st != 0) return;
+        // Cotangent staging, executed by the CTA's last warp (which owns no rows), two levels deep: the row of reverse level
+        // tr is fetched from HBM with fire-and-forget 4-byte cp.async into s_raw[buf] while the level before it is being
+        // swept, and summed per padded column (receivers may share a column) into s_cot[buf] one level later.  Nothing on
+        // the way waits for an HBM round trip: fetched by dependent loads, the row cost ~10 000 cycles per level on
+        // Marmousi-width grids -- more than the sweep (tools/trace_levels.py).
+        auto fetch_cot = [&](const int tr, const int buf) {
+            if (tr < 0 || tr % a.st != 0) return;
             const float *gt = a.cot + ((size_t)gshot * g.nt_out + tr / a.st) * g.nrec;
+            float *dst = s_raw + buf * g.nrec;
+            for (int r = lane_id; r < g.nrec; r += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + r)), "l"(gt + r) : "memory");
+        };
+        auto sum_cot = [&](const int tr, const int buf) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            if (tr < 0 || tr % a.st != 0) return;
+            const float *raw = s_raw + buf * g.nrec;
+            float *dst = s_cot + buf * g.nxp;
+#pragma unroll 4
             for (int xx = lane_id; xx < g.nxp; xx += 32) {
                 float acc = 0.0f;
-                for (int k = s_rec_ptr[xx]; k < s_rec_ptr[xx + 1]; ++k) acc += gt[s_rec_idx[k]];
+                for (int k = s_rec_ptr[xx]; k < s_rec_ptr[xx + 1]; ++k) acc += raw[s_rec_idx[k]];
                 dst[xx] = acc;
             }
         };
-        if (ADJ && tid >= NT - 32 && has_rec_row) stage_cot(a.nt - 1, 0);  // level 0 of the loop is reverse time nt-1
+        if (ADJ && tid >= NT - 32 && has_rec_row) {  // level 0 of the loop is reverse time nt-1
+            fetch_cot(a.nt - 1, 0);
+            sum_cot(a.nt - 1, 0);
+            fetch_cot(a.nt - 2, 1);
+        }
         __syncthreads();
         cluster_sync_all();  // shot boundary: every CTA has finished the previous shot and cleared its buffers
 
@@ -297,10 +317,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
             stamp(t, 1);
             const int p0 = prv + 2 * pitch + th.x;
             const int trev = a.nt - 1 - t;  // adjoint mode: the reverse-time level this iteration computes
-            // The cotangent of the NEXT reverse level is staged (summed per column) in shared memory by the CTA's last
-            // warp while the others sweep: fetched by the owner threads themselves, the dependent global loads stalled
-            // their in-order sweep by ~2500 cycles per level on the cluster's critical path (tools/trace_levels.py).
-            if (ADJ && tid >= NT - 32 && has_rec_row && t + 1 < a.nt) stage_cot(trev - 1, (t + 1) & 1);
+            // cotangent pipeline of the last warp: sum the row of the NEXT reverse level (fetched one level ago), then fetch
+            // the row of the level after it
+            if (ADJ && tid >= NT - 32 && has_rec_row && t + 1 < a.nt) {
+                sum_cot(trev - 1, (t + 1) & 1);
+                fetch_cot(trev - 2, t & 1);
+            }
             if (warp_active) {
                 const uint64_t *push_bar = bars + 2 * pbuf + hp.bar;  // barrier of the buffer written now, at the receiver
                 if (rev) fwd_sweep<RMAX, PITCH, -1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
@@ -349,7 +371,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
             // usually owns no rows -- from the finished level while the other warps already sweep the next one (that
             // buffer is read-only until the barrier after next).  In the owner threads' epilogue it sat on the critical
             // path of the whole cluster: ~1900 of 9000 cycles per level (tools/trace_levels.py).
-            if (!ADJ && tid >= NT - 32 && t % a.st == 0 && g.igz >= r0 && g.igz < r0 + nrows) {
+            if (!ADJ && a.seis != nullptr && tid >= NT - 32 && t % a.st == 0 && g.igz >= r0 && g.igz < r0 + nrows) {
                 float *seis_t = a.seis + ((size_t)gshot * g.nt_out + t / a.st) * g.nrec;
                 const float *row = smem + prv + (2 + g.igz - r0) * pitch;
                 for (int xx = lane_id; xx < g.nxp; xx += 32)
@@ -389,7 +411,7 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg)
         const int ngroups = (maxrows + kClusterRowsMax - 1) / kClusterRowsMax;  // each thread marches kClusterRowsMax rows
         if (ngroups > groups_max) continue;
         const int slabrows = ngroups * kClusterRowsMax;  // >= maxrows: rows past the slab are computed but never stored
-        size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + g.nxp + 1 + g.nrec + 2 * g.nxp) * sizeof(float);
+        size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + g.nxp + 1 + g.nrec + 2 * g.nxp + 2 * g.nrec) * sizeof(float);
         if (smem > (size_t)max_smem) continue;
         const size_t room = nthreads == 256 ? (size_t)(113 * 1024) : (size_t)max_smem;  // two CTAs per SM must fit 228 KB
         if (nthreads == 256 && smem > room) continue;
@@ -403,7 +425,7 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg)
 }
 
 template <int PITCH, bool ADJ, int NT>
-static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
+static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st, int *wave_only)
 {
     auto kernel = k_fwd_cluster<kClusterRowsMax, PITCH, ADJ, NT>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
@@ -430,6 +452,7 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
     e = cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg);
     if (e != cudaSuccess) return e;
     if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
+    if (wave_only != nullptr) { *wave_only = max_clusters; return cudaSuccess; }
     const int ncl = max_clusters < a.nshots ? max_clusters : a.nshots;
     cfg.gridDim = dim3((unsigned)(ncl * cc.C));
     e = cudaLaunchKernelEx(&cfg, kernel, a, p.g);
@@ -437,18 +460,40 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
     return e;
 }
 
-cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
+static cudaError_t dispatch_fwd_cluster(const Plan &p, const ClusterConfig &cc, const ClusterFwdArgs &a, cudaStream_t st, int *wave_only)
 {
     const bool adj = a.adj_mode != 0;
     if (cc.nthreads == 256) {  // two CTAs per SM (experimental; OpenFWI pitch and runtime pitch only)
-        if (p.g.pitch == 312) return adj ? launch_fwd_cluster_t<312, true, 256>(p, cc, a, st) : launch_fwd_cluster_t<312, false, 256>(p, cc, a, st);
-        return adj ? launch_fwd_cluster_t<0, true, 256>(p, cc, a, st) : launch_fwd_cluster_t<0, false, 256>(p, cc, a, st);
+        if (p.g.pitch == 312) return adj ? launch_fwd_cluster_t<312, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<312, false, 256>(p, cc, a, st, wave_only);
+        return adj ? launch_fwd_cluster_t<0, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<0, false, 256>(p, cc, a, st, wave_only);
     }
     switch (p.g.pitch) {  // production grids get immediate row offsets (OpenFWI 310+2, Marmousi/Overthrust 430+2)
-        case 312: return adj ? launch_fwd_cluster_t<312, true, 512>(p, cc, a, st) : launch_fwd_cluster_t<312, false, 512>(p, cc, a, st);
-        case 432: return adj ? launch_fwd_cluster_t<432, true, 512>(p, cc, a, st) : launch_fwd_cluster_t<432, false, 512>(p, cc, a, st);
-        default: return adj ? launch_fwd_cluster_t<0, true, 512>(p, cc, a, st) : launch_fwd_cluster_t<0, false, 512>(p, cc, a, st);
+        case 312: return adj ? launch_fwd_cluster_t<312, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<312, false, 512>(p, cc, a, st, wave_only);
+        case 432: return adj ? launch_fwd_cluster_t<432, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<432, false, 512>(p, cc, a, st, wave_only);
+        default: return adj ? launch_fwd_cluster_t<0, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<0, false, 512>(p, cc, a, st, wave_only);
     }
+}
+
+cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
+{
+    return dispatch_fwd_cluster(p, cc, a, st, nullptr);
+}
+
+// Clusters of this configuration that are co-resident on the device = shots in flight per "wave" of the persistent
+// kernel (33 four-CTA clusters, 24 six-CTA clusters on a 148-SM B200: whole clusters per GPC).  Falls back to
+// SMs / C when the occupancy query is not available (no device).
+int fwd_cluster_wave(const Plan &p, const ClusterConfig &cc)
+{
+    ClusterFwdArgs a{};
+    a.adj_mode = 1;
+    int wave = 0;
+    if (dispatch_fwd_cluster(p, cc, a, nullptr, &wave) != cudaSuccess || wave < 1) {
+        cudaGetLastError();
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+        wave = sms / cc.C > 0 ? sms / cc.C : 1;
+    }
+    return wave;
 }
 
 }  // namespace rdfwi

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(kImgThreads) k_imaging(const float *__restrict
                                                          const float *__restrict__ alpha, const float *__restrict__ kap,
                                                          const float *__restrict__ beta_src, const float *__restrict__ Gb,
                                                          const int *__restrict__ isx, float *__restrict__ Ga,
-                                                         float *__restrict__ Gk, Grid g, int nt, int shot0, int prefetch)
+                                                         float *__restrict__ Gk, Grid g, int nt, int shot0, int pshot0, int prefetch)
 {
     const int i = blockIdx.x * kImgThreads + threadIdx.x;  // float4 slot
     if (i >= g.nzp * g.q4) return;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kImgThreads) k_imaging(const float *__restrict
     const int z = i / g.q4, x = (i - z * g.q4) * 4;
     const size_t cell = (size_t)i * 4;
     const size_t lvl = g.level;
-    const float *pl = phist + (size_t)shot * nt * lvl + (size_t)(nt - 1) * lvl + cell;  // p_m, m = nt-1 .. 0
+    const float *pl = phist + (size_t)(shot - pshot0) * nt * lvl + (size_t)(nt - 1) * lvl + cell;  // p_m, m = nt-1 .. 0
     const float *ul = uhist + (size_t)shot_l * nt * lvl + cell;                         // u_m = slot nt-1-m
 
     // kappa*dt of the four cells (columns override rows, solvers/pde.py:48-51)
@@ -105,14 +105,17 @@ __global__ void __launch_bounds__(kImgThreads) k_imaging(const float *__restrict
 
 }  // namespace
 
+// phist holds the forward history of shots pshot0, pshot0+1, ... (0 = the whole batch's history; shot0 = a chunk-local
+// history recomputed in the backward pass)
 cudaError_t launch_imaging(const Plan &p, const float *phist, const float *uhist, const float *alpha, const float *kap,
-                           const float *beta_src, const float *Gb, float *Ga, float *Gk, int shot0, int nshots, cudaStream_t st)
+                           const float *beta_src, const float *Gb, float *Ga, float *Gk, int shot0, int nshots, int pshot0,
+                           cudaStream_t st)
 {
     const Grid &g = p.g;
     const int slots = g.nzp * g.q4;
     const dim3 grid((slots + kImgThreads - 1) / kImgThreads, nshots);
     const int pf = p.img_prefetch > 0 ? p.img_prefetch : 4;
-    k_imaging<<<grid, kImgThreads, 0, st>>>(phist, uhist, alpha, kap, beta_src, Gb, p.d_isx, Ga, Gk, g, p.nt, shot0, pf);
+    k_imaging<<<grid, kImgThreads, 0, st>>>(phist, uhist, alpha, kap, beta_src, Gb, p.d_isx, Ga, Gk, g, p.nt, shot0, pshot0, pf);
     count_launch();
     return cudaGetLastError();
 }

@@ -111,9 +111,19 @@ struct Workspace {
     int g_planes = 1;
     float *seg_hist = nullptr;
     bool split = false;
+    bool fused = false;       // fused cluster-resident adjoint (k_adj_cluster) when the split adjoint is not used
+    bool recompute = false;   // split adjoint on a forward history recomputed chunk by chunk (history_segment >= nt)
     int u_chunk = 0;
     float *u_hist = nullptr;
+    float *p_hist = nullptr;  // recompute mode: forward history of one chunk of shots
 };
+
+int cached_wave(const Plan &p, const ClusterConfig &cc)
+{
+    const int key = cc.C * 1024 + cc.nthreads;
+    if (p.wave_key != key) { p.wave_val = fwd_cluster_wave(p, cc); p.wave_key = key; }
+    return p.wave_val;
+}
 
 Workspace carve(const Plan &p, int B, void *base)
 {
@@ -136,24 +146,36 @@ Workspace carve(const Plan &p, int B, void *base)
     w.minpart = (float *)take((size_t)B * kMinBlocks * 2 * 4);
     w.fields = (float *)take(3 * w.chunk_level * 4);
     w.zero = (float *)take(w.chunk_level * 4);
-    ClusterConfig acc;
+    ClusterConfig acc, fcc;
     // split adjoint (cluster u-field kernel + streaming imaging kernel) whenever the forward cluster kernel fits;
-    // else the fused cluster adjoint; checkpointed histories run on the per-level engine
-    const bool cluster_ok = p.engine != 1 && p.history_segment == 0;
-    const bool fused_ok = cluster_ok && adj_cluster_config(p, &acc);
-    w.split = cluster_ok && p.adj_mode == 0 && cluster_config(p, &acc);
+    // else the fused cluster adjoint; histories checkpointed in time run on the per-level engine.  history_segment >= nt
+    // (a single segment: nothing is kept) runs the split adjoint on a forward history recomputed chunk by chunk.
+    const bool single_segment = p.history_segment >= p.nt;
+    const bool cluster_ok = p.engine != 1 && (p.history_segment == 0 || single_segment);
+    const bool fused_ok = cluster_ok && !single_segment && adj_cluster_config(p, &acc);
+    w.split = cluster_ok && (p.adj_mode == 0 || single_segment) && cluster_config(p, &fcc);
+    w.recompute = w.split && single_segment;
     w.u_chunk = 0;
     if (w.split) {
-        // shots whose adjoint-field history is in flight at once: two waves of 33 four-CTA clusters, evened out over the
-        // chunks, and at most ~40 GB of scratch; long records that leave less than a wave per chunk use the fused kernel
+        // Shots whose adjoint-field history is in flight at once: whole waves of co-resident clusters (33 four-CTA or 24
+        // six-CTA clusters per wave), two waves when the scratch cap allows, evened out over the chunks; long records
+        // that leave less than a wave per chunk use the fused kernel when that exists.
         const int nshots = B * g.ns;
+        const int wave = cached_wave(p, fcc);
         const double per_shot = (double)p.nt * (double)g.level * sizeof(float);
-        int chunk = p.u_chunk_shots > 0 ? p.u_chunk_shots : std::min(66, std::max(1, (int)(40e9 / per_shot)));
+        // cap on one scratch history: 40 GB beside a full forward history, 55 GB each for the two of the recompute tier
+        const double cap = p.scratch_mb > 0 ? 1e6 * (double)p.scratch_mb : (single_segment ? 55e9 : 40e9);
+        int chunk = p.u_chunk_shots;
+        if (chunk <= 0) {
+            const int fit = std::max(1, (int)(cap / per_shot));
+            chunk = fit >= 2 * wave ? 2 * wave : (fit >= wave ? wave : fit);
+        }
         chunk = std::min(chunk, nshots);
         const int nchunks = (nshots + chunk - 1) / chunk;
         w.u_chunk = (nshots + nchunks - 1) / nchunks;
-        if (p.u_chunk_shots == 0 && w.u_chunk < nshots && w.u_chunk < 24 && fused_ok) { w.split = false; w.u_chunk = 0; }
+        if (p.u_chunk_shots == 0 && !single_segment && w.u_chunk < nshots && w.u_chunk < wave && fused_ok) { w.split = false; w.u_chunk = 0; }
     }
+    w.fused = fused_ok && !w.split;
     // imaging planes per model: one per shot for the cluster engines, one per grid.z slice for the per-level adjoint
     w.g_planes = (w.split || fused_ok) ? g.ns : adj_shot_slices(p, w.nb);
     w.Ga = (float *)take((size_t)B * w.g_planes * g.level * 4);
@@ -162,9 +184,10 @@ Workspace carve(const Plan &p, int B, void *base)
     w.fold_tmp = (float *)take((size_t)B * g.nz * g.nxp * 4);
     w.vel_part = (double *)take((size_t)B * kMinBlocks * 8);
     // checkpoint mode: the levels of one segment of one chunk, recomputed during the backward pass
-    w.seg_hist = p.history_segment > 0 ? (float *)take(w.chunk_level * (size_t)(p.history_segment - 1) * 4) : nullptr;
-    // split adjoint: adjoint-field history of one chunk of shots
+    w.seg_hist = (p.history_segment > 0 && !w.recompute) ? (float *)take(w.chunk_level * (size_t)(p.history_segment - 1) * 4) : nullptr;
+    // split adjoint: adjoint-field history of one chunk of shots (+ the recomputed forward history of the chunk)
     if (w.split) w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
+    if (w.recompute) w.p_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
     w.bytes = off;
     return w;
 }
@@ -316,6 +339,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "adj_mode") { if (value < 0 || value > 1) goto bad; p->adj_mode = (int)value; }
     else if (k == "timing") { clear_spans(p); p->timing = value != 0; }  // (re)starts the per-kernel-class timers
     else if (k == "u_chunk_shots") { if (value < 0) goto bad; p->u_chunk_shots = (int)value; }
+    else if (k == "scratch_mb") { if (value < 0) goto bad; p->scratch_mb = value; }
     else if (k == "cluster_threads") { if (value != 0 && value != 256 && value != 512) goto bad; p->cluster_threads = (int)value; }
     else if (k == "img_prefetch") { if (value < 0 || value > 64) goto bad; p->img_prefetch = (int)value; }
     else if (k == "trace_ptr") { p->trace_ptr = reinterpret_cast<long long *>(value); }
@@ -349,6 +373,10 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
         *out = want_us ? (int64_t)(us + 0.5) : n;
     }
     else if (k == "adj_split") *out = p->last_split;
+    else if (k == "u_chunk_shots") *out = p->u_chunk_shots;
+    else if (k == "u_chunk_used") *out = p->last_u_chunk;
+    else if (k == "scratch_mb") *out = p->scratch_mb;
+    else if (k == "cluster_wave") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cached_wave(*p, cc) : 0; }
     else if (k == "cluster_size") *out = p->cluster_size;
     else if (k == "cluster_size_used") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cc.C : 0; }
     else if (k == "adj_cluster_size_used") { ClusterConfig cc; *out = adj_cluster_config(*p, &cc) ? cc.C : 0; }
@@ -407,6 +435,7 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
     RD_CUDA(launch_coefficients(p, v, B, w.alpha, w.kap, w.velmin, w.argmin, w.beta_src, w.minpart, st));
     float *hist = static_cast<float *>(history);
     const int nt = p.nt;
+    if (hist && w.recompute) hist = nullptr;  // nothing is kept: the backward pass recomputes the forward field
     const bool ckpt = hist && segment > 0;  // checkpointed history: per-level engine
     ClusterConfig cc;
     if (p.engine != 1 && !ckpt && cluster_config(p, &cc)) {
@@ -491,10 +520,11 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     RD_CUDA(launch_coefficients(p, v, B, w.alpha, w.kap, w.velmin, w.argmin, w.beta_src, w.minpart, st));
     const float *hist = static_cast<const float *>(history);
     const int nt = p.nt;
-    const bool ckpt = segment > 0;
+    const bool ckpt = segment > 0 && !w.recompute;
     RD_CUDA(cudaMemsetAsync(w.Gb, 0, (size_t)B * g.ns * sizeof(float), st));
     ClusterConfig cc;
-    const_cast<Plan &>(p).last_split = (!ckpt && w.split) ? 1 : 0;
+    const_cast<Plan &>(p).last_split = (!ckpt && w.split) ? (w.recompute ? 2 : 1) : 0;
+    const_cast<Plan &>(p).last_u_chunk = w.u_chunk;
     if (!ckpt && w.split && cluster_config(p, &cc)) {
         // split adjoint: per chunk of shots, (1) the cluster-resident kernel runs the adjoint field in the u-variable
         // and streams it to HBM, (2) a streaming kernel forms the imaging sums from the two histories
@@ -504,20 +534,25 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
             ClusterFwdArgs a{};
             a.alpha = w.alpha; a.kap = w.kap; a.beta_src = w.beta_src;
             a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx; a.wavelet = p.d_wavelet;
-            a.seis = nullptr; a.hist = w.u_hist;
-            a.nshots = n; a.nt = nt; a.st = p.st;
-            a.shot0 = s0; a.adj_mode = 1; a.cot = cot; a.Gb = w.Gb; a.trace = p.trace_ptr;
+            a.nshots = n; a.nt = nt; a.st = p.st; a.shot0 = s0; a.trace = p.trace_ptr;
+            if (w.recompute) {  // forward field of the chunk, again, this time keeping every level (no seismograms)
+                a.seis = nullptr; a.hist = w.p_hist; a.adj_mode = 0;
+                Timed timed(p, 0, st);
+                RD_CUDA(launch_fwd_cluster(p, cc, a, st));
+            }
+            a.seis = nullptr; a.hist = w.u_hist; a.adj_mode = 1; a.cot = cot; a.Gb = w.Gb;
             {
                 Timed timed(p, 1, st);
                 RD_CUDA(launch_fwd_cluster(p, cc, a, st));
             }
             Timed timed(p, 2, st);
-            RD_CUDA(launch_imaging(p, hist, w.u_hist, w.alpha, w.kap, w.beta_src, w.Gb, w.Ga, w.Gk, s0, n, st));
+            RD_CUDA(launch_imaging(p, w.recompute ? w.p_hist : hist, w.u_hist, w.alpha, w.kap, w.beta_src, w.Gb, w.Ga, w.Gk, s0, n,
+                                   w.recompute ? s0 : 0, st));
         }
         RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
         return RDFWI_OK;
     }
-    if (!ckpt && w.g_planes > 1 && adj_cluster_config(p, &cc)) {
+    if (!ckpt && w.fused && adj_cluster_config(p, &cc)) {
         // cluster-resident reverse-time loop: one launch for all shots and all levels
         ClusterAdjArgs a{};
         a.alpha = w.alpha; a.kap = w.kap; a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
@@ -599,8 +634,8 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
         }
     }
     delete timed_adj;
-    // (when g_planes > 1 but the per-level engine ran, only plane 0 of each model was accumulated into)
-    RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, 1, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
+    // the per-level engine accumulated into pl_slices planes per model (one per grid.z slice of shots)
+    RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, pl_slices, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
     return RDFWI_OK;
 }
 

@@ -65,6 +65,7 @@ struct Plan {
     int cluster_threads = 0;  // 0/512 = one 512-thread CTA per SM; 256 = two 256-thread CTAs per SM (k_fwd_cluster)
     int img_prefetch = 0;     // imaging kernel: levels ahead pulled into L2 (0 = default 4)
     long long *trace_ptr = nullptr;  // debug: device buffer for per-warp timeline stamps of k_fwd_cluster
+    int last_u_chunk = 0;     // shots per chunk of the last split adjoint
     int last_split = 0;       // whether the last rdfwi_backward ran the split adjoint (reported by rdfwi_plan_get "adj_split")
     int u_chunk_shots = 0;    // shots whose adjoint-field history is in flight at once in split mode (0 = auto)
     // optional per-kernel-class timing with CUDA events on the caller's stream (rdfwi_plan_set "timing")
@@ -72,6 +73,9 @@ struct Plan {
     struct Span { cudaEvent_t a, b; int kind; };
     std::vector<Span> spans;  // kind: 0 forward time loop, 1 adjoint-field time loop, 2 imaging, 3 fused / per-level adjoint loop
     int history_segment = 0;  // 0 = keep every level; K >= 3 = checkpoint pairs every K levels, recompute in the backward pass
+                              // (K >= nt: no history at all -- the backward pass recomputes the forward field chunk by chunk)
+    long long scratch_mb = 0; // cap on ONE scratch history of the split adjoint, MB (0 = 40000)
+    mutable int wave_key = -1, wave_val = 0;  // cached fwd_cluster_wave() of the configuration in use
 };
 
 // Cluster-resident forward time loop (kernels_cluster.cu).
@@ -172,12 +176,14 @@ int adj_shot_slices(const Plan &p, int nb);  // imaging planes per model the per
 // kernels_cluster.cu
 bool cluster_config(const Plan &p, ClusterConfig *cfg);
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st);
+int fwd_cluster_wave(const Plan &p, const ClusterConfig &cc);  // co-resident clusters = shots in flight per wave
 // kernels_cluster_adj.cu
 bool adj_cluster_config(const Plan &p, ClusterConfig *cfg);
 cudaError_t launch_adj_cluster(const Plan &p, const ClusterConfig &cc, ClusterAdjArgs a, cudaStream_t st);
 // kernels_imaging.cu: zero-lag imaging sums of `nshots` shots from the forward history and the adjoint-field history
 cudaError_t launch_imaging(const Plan &p, const float *phist, const float *uhist, const float *alpha, const float *kap,
-                           const float *beta_src, const float *Gb, float *Ga, float *Gk, int shot0, int nshots, cudaStream_t st);
+                           const float *beta_src, const float *Gb, float *Ga, float *Gk, int shot0, int nshots, int pshot0,
+                           cudaStream_t st);
 // kernels_epilogue.cu  (planes = imaging planes per model: 1 for the per-level engine, ns for the cluster engine)
 cudaError_t launch_gradient_epilogue(const Plan &p, const float *v, int B, const float *Ga, const float *Gk,
                                      const float *Gb, int planes, const int *argmin, float *fold_tmp,

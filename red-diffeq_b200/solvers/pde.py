@@ -175,28 +175,50 @@ class FWIForward(nn.Module):
         self._segment = segment
 
     def _choose_segment(self, plan, B, device):
-        """History policy of one forward/backward pair.  Automatic mode walks three tiers until the buffers fit the
-        free HBM: (1) every level + split adjoint (needs a scratch history of the adjoint field), (2) every level +
-        fused cluster adjoint (no scratch), (3) checkpointed history on the per-level engine."""
+        """History policy of one forward/backward pair.  Automatic mode walks the tiers until the buffers fit the free
+        HBM: (1) every level + split adjoint (needs a scratch history of the adjoint field); (2) no history at all:
+        the backward pass recomputes the forward field chunk by chunk on the cluster engine (segment = nt, one extra
+        forward, two scratch histories of one or two waves of shots); (3) every level + fused cluster adjoint (no
+        scratch); (4) history checkpointed in time on the per-level engine."""
         seg = self._segment
         key = (id(plan), B)
         if seg is None and key in self._segment_auto:   # decided once per (plan, batch): cudaMemGetInfo is slow
-            seg, adj_mode = self._segment_auto[key]
-            if adj_mode is not None:
-                plan.set("adj_mode", adj_mode)
+            seg, extra = self._segment_auto[key]
+            for k, v in extra.items():
+                plan.set(k, v)
         elif seg is None:
             free, _total = torch.cuda.mem_get_info(device)
             idle = sum(b.numel() for b in self._history_arena.get(str(device), []))
             budget = 0.9 * (free + idle + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device))
-            seg, adj_mode = 0, None
-            plan.set("history_segment", 0)
-            if plan.history_bytes(B, 0) + plan.workspace_bytes(B) > budget:
-                if "adj_mode" not in self.options:
-                    adj_mode = 1
-                    plan.set("adj_mode", 1)
-                if adj_mode is None or plan.history_bytes(B, 0) + plan.workspace_bytes(B) > budget:
-                    seg = max(3, int(np.ceil(np.sqrt(2.0 * plan.nt))))   # minimises pairs + segment levels
-            self._segment_auto[key] = (seg, adj_mode)
+
+            def fits(segment, **extra):
+                plan.set("history_segment", segment)
+                for k, v in extra.items():
+                    plan.set(k, v)
+                return plan.history_bytes(B, segment) + plan.workspace_bytes(B) <= budget
+
+            user = self.options
+            clustered = user.get("engine", 0) != 1 and plan.get("cluster_size_used") > 0
+            wave = plan.get("cluster_wave") if clustered else 0
+            tiers = [(0, {})]
+            if clustered and "adj_mode" not in user:
+                # a record so long that the scratch history of the split adjoint holds less than a wave of shots makes
+                # the library fall back to the fused adjoint kernel: recomputing is faster than that
+                per_shot = 4.0 * plan.nt * plan.level_floats()
+                if int(40e9 // per_shot) < min(wave, B * plan.ns):
+                    tiers = []
+                tiers.append((plan.nt, {}))
+                if "u_chunk_shots" not in user:
+                    tiers.append((plan.nt, {"u_chunk_shots": wave}))
+                tiers += [(0, {}), (0, {"adj_mode": 1})]
+            seg, extra = max(3, int(np.ceil(np.sqrt(2.0 * plan.nt)))), {}   # minimises pairs + segment levels
+            for cand_seg, cand_extra in tiers:
+                if fits(cand_seg, **cand_extra):
+                    seg, extra = cand_seg, cand_extra
+                    break
+                for k in cand_extra:   # undo the tier's options before trying the next one
+                    plan.set(k, user.get(k, 0))
+            self._segment_auto[key] = (seg, extra)
         plan.set("history_segment", seg)
         return seg
 

@@ -92,6 +92,7 @@ def test_checkpointed_history_matches_full_history(name, segment):
     full.set_option("engine", 1)
     full.set_history_segment(0)
     ck = _op(g)
+    ck.set_option("engine", 1)     # (segment >= nt on the cluster engine is the recompute tier, tested below)
     ck.set_history_segment(segment)
     shape = (g.v.shape[0], len(full.ctx["sx"]), -(-g.ctx["nt"] // g.sample_temporal), len(full.ctx["gx"]))
     cot = g.cotangent(shape)
@@ -100,6 +101,56 @@ def test_checkpointed_history_matches_full_history(name, segment):
     assert np.array_equal(s0, s1)
     assert np.array_equal(g0, g1)
     assert rel_l2(g1, g.grad_f32) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("name", ["tiny_default", "tiny_custom", "tiny_half_receivers", "openfwi"])
+@pytest.mark.parametrize("chunk", [0, 2])
+def test_recomputed_history_matches_full_history(name, chunk):
+    """No history kept (segment = nt): the backward pass recomputes the forward field chunk by chunk on the cluster
+    engine and runs the split adjoint on it -- same kernels, same order => bit-identical to the full-history run."""
+    g = Golden(name)
+    full = _op(g)
+    full.set_option("engine", 2)
+    full.set_history_segment(0)
+    rc = _op(g)
+    rc.set_option("engine", 2)
+    if chunk:
+        rc.set_option("u_chunk_shots", chunk)
+    rc.set_history_segment(g.ctx["nt"])
+    shape = (g.v.shape[0], len(full.ctx["sx"]), -(-g.ctx["nt"] // g.sample_temporal), len(full.ctx["gx"]))
+    cot = g.cotangent(shape)
+    s0, g0 = _run(full, g.v, cot)
+    s1, g1 = _run(rc, g.v, cot)
+    plan = rc._plan_for(g.v.shape[2], g.v.shape[3], torch.device("cuda:0"))
+    assert plan.get("adj_split") == 2 and plan.history_bytes(g.v.shape[0], g.ctx["nt"]) == 0
+    assert np.array_equal(s0, s1)
+    assert np.array_equal(g0, g1)
+    assert rel_l2(g1, g.grad_f32) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("engine", ["per-level", "per-level-checkpointed", "cluster-split", "cluster-fused"])
+def test_many_shots_per_model(engine, oracle):
+    """More shots than any golden case (ns = 11: the per-level adjoint deals them over several grid.z slices, each with its
+    own imaging plane; the cluster engines run more shots than fit one chunk)."""
+    from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize
+    from red_diffeq_b200.utils import synthetic
+    nz, nx, B = 20, 28, 2
+    ctx = dict(n_grid=nx, nt=130, dx=10.0, dt=0.001, nbc=12, f=25.0, sz=10, gz=10, ng=nx, ns=11)
+    sv = oracle.Survey(dict(ctx), nz, nx)
+    vn = synthetic.velocity_models(B, nz, nx, seed=31)
+    cot = synthetic.cotangent((B, sv.ns, sv.nt_out, sv.nrec), seed=32)
+    op = FWIForward(dict(ctx), "cuda:0", normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    op.set_option("engine", 1 if engine.startswith("per-level") else 2)
+    op.set_option("adj_mode", 1 if engine == "cluster-fused" else 0)
+    if engine == "cluster-split":
+        op.set_option("u_chunk_shots", 7)
+    if engine == "per-level-checkpointed":
+        op.set_history_segment(16)
+    seis, grad = _run(op, vn, cot)
+    v_phys = (vn + np.float32(1)) / np.float32(2) * np.float32(3000) + np.float32(1500)
+    seis_o, grad_o = oracle.gradient(sv, v_phys, cot)
+    assert np.array_equal(seis, seis_o)
+    assert rel_l2(grad, grad_o * 1500.0) <= GRAD_TOL
 
 
 def test_coefficients_bit_identical(oracle):

@@ -1,21 +1,25 @@
-"""Per-warp timeline of the cluster-resident forward kernel (debug): python tools/trace_levels.py [B]"""
+"""Per-warp timeline of the cluster-resident forward kernel (debug): python tools/trace_levels.py [B] [fwd|adj] [openfwi|marmousi]"""
 import os, sys, numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize
 from red_diffeq_b200.utils import synthetic
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-ctx = dict(synthetic.PDE_OPENFWI); ctx["nt"] = 300
+mode = sys.argv[2] if len(sys.argv) > 2 else "fwd"
+kind = sys.argv[3] if len(sys.argv) > 3 else "openfwi"
+ctx = dict(synthetic.PDE_OPENFWI if kind == "openfwi" else synthetic.PDE_MARMOUSI); ctx["nt"] = 300
+nz, nx = (70, 70) if kind == "openfwi" else (70, 190)
 op = FWIForward(ctx, "cuda:0", normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
-trace = torch.zeros((4, 4, 16, 6), dtype=torch.int64, device="cuda:0")   # [cta][level][warp][phase]
+trace = torch.zeros((16, 4, 16, 6), dtype=torch.int64, device="cuda:0")   # [cta][level][warp][phase]
 op.set_option("trace_ptr", trace.data_ptr())
-v = torch.tensor(synthetic.velocity_models(B, 70, 70), device="cuda:0", requires_grad=True)
+v = torch.tensor(synthetic.velocity_models(B, nz, nx), device="cuda:0", requires_grad=True)
 s = op(v); torch.cuda.synchronize()
-if len(sys.argv) > 2 and sys.argv[2] == "adj":      # trace the adjoint-field launch (k_fwd_cluster<ADJ>) instead
+C = op._plan_for(nz, nx, torch.device("cuda:0")).get("cluster_size_used")
+if mode == "adj":      # trace the adjoint-field launch (k_fwd_cluster<ADJ>) instead
     trace.zero_()
     s.backward(torch.ones_like(s)); torch.cuda.synchronize()
 tr = trace.cpu().numpy().astype(np.int64)
 names = ["start", "after halo wait", "after sweep", "after epilogue", "at barrier", "after barrier"]
-for cta in range(4):
+for cta in range(C):
     t0 = tr[cta, 1, :, 0].min()   # level 101 as origin
     print(f"CTA {cta}: level 101, cycles relative to the earliest warp start; per warp: " + ", ".join(names[1:]))
     for w in range(16):
