@@ -36,10 +36,10 @@ WORKLOADS = {
     "openfwi_b1": ("openfwi", 70, 70, 1),         # configs[0]
     "marmousi_b1": ("marmousi", 70, 190, 1),      # configs[2] shape, reference shot count (5)
     "marmousi_b16": ("marmousi", 70, 190, 16),
-    # configs[2]: ONE Marmousi-shaped model, 192 shots (the reference's 5 do not divide over 8 GPUs; 192 =
-    # 8 GPUs x one wave of 24 six-CTA clusters) sharded over the ranks by ShardedFWIForward: strong scaling, one
-    # gradient all-reduce per step
-    "marmousi_sharded": ("marmousi192", 70, 190, 1),
+    # configs[2]: ONE Marmousi-shaped model, 176 shots (the reference's 5 do not divide over 8 GPUs; 176 =
+    # 8 GPUs x one wave of 22 co-resident six-CTA clusters, what cudaOccupancyMaxActiveClusters reports on a B200)
+    # sharded over the ranks by ShardedFWIForward: strong scaling, one gradient all-reduce per step
+    "marmousi_sharded": ("marmousi176", 70, 190, 1),
     # configs[3]: Overthrust shape (= the Marmousi grid in the reference's configs) with a long record, nt = 4000
     # (synthetic extension); run with --history-segment K to exercise wavefield checkpointing
     "overthrust_long": ("overthrust4000", 70, 190, 8),
@@ -64,8 +64,8 @@ def make_ctx(kind):
     if kind == "openfwi":
         return dict(synthetic.PDE_OPENFWI)
     ctx = dict(synthetic.PDE_MARMOUSI)
-    if kind == "marmousi192":
-        ctx["ns"] = 192
+    if kind == "marmousi176":
+        ctx["ns"] = 176
     if kind == "overthrust4000":
         ctx["nt"] = 4000
     return ctx
@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--workload", default="openfwi_b64", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override models per GPU (debugging)")
     ap.add_argument("--nt", type=int, default=0, help="override time levels (debugging; invalidates the headline)")
+    ap.add_argument("--ns", type=int, default=0, help="override shots per model (debugging; invalidates the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (e.g. chunk_models=8)")
     ap.add_argument("--history-segment", type=int, default=None,
@@ -216,11 +217,13 @@ def main():
     ctx = make_ctx(kind)
     if args.nt:
         ctx["nt"] = args.nt
+    if args.ns:
+        ctx["ns"] = args.ns
     sharded = args.workload == "marmousi_sharded"
     ns, nt, nbc = ctx["ns"], ctx["nt"], ctx["nbc"]
     nzp, nxp = nz + 2 * nbc, nx + 2 * nbc
     if sharded:
-        # strong scaling: the same 1 x 192 shots whatever the rank count; every rank models its shots
+        # strong scaling: the same 1 x 176 shots whatever the rank count; every rank models its shots
         wrapper = ShardedFWIForward(dict(ctx), dev, mode="shots", normalize=True, v_denorm_func=v_denormalize,
                                     s_norm_func=s_normalize_none)
         _, _, my_shots = wrapper.partition(B)

@@ -13,6 +13,8 @@
 //   4. an elected thread streams the slab to the wavefield history with a 1-D bulk copy
 //      (cp.async.bulk shared -> global), overlapped with the next level.
 // HBM traffic: forward = the history write only (4 B / cell-update instead of 12).
+#include <mutex>
+
 #include "cluster_ptx.cuh"
 
 namespace rdfwi {
@@ -428,13 +430,7 @@ template <int PITCH, bool ADJ, int NT>
 static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st, int *wave_only)
 {
     auto kernel = k_fwd_cluster<kClusterRowsMax, PITCH, ADJ, NT>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
-    if (e != cudaSuccess) return e;
     a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
-    if (cc.C > 8) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return e;
-    }
 
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
@@ -444,14 +440,39 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = cc.smem;
     cfg.stream = st;
-    // persistent: as many clusters as can be co-resident (or one per shot if fewer shots)
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
-    cfg.gridDim = dim3((unsigned)(sms / cc.C * cc.C));
-    int max_clusters = 0;
-    e = cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg);
-    if (e != cudaSuccess) return e;
-    if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
+    // persistent: as many clusters as can be co-resident (or one per shot if fewer shots).  The function attributes and
+    // the occupancy answer are set / asked once per (instantiation, device, cluster size, shared memory).
+    static std::mutex mu;                       // function attributes are per (function, device): raise them monotonically
+    static size_t smem_set[64] = {0};
+    static bool nonportable_set[64] = {false};
+    static thread_local int c_dev = -1, c_C = 0, c_max = 0;
+    static thread_local size_t c_smem = 0;
+    cudaError_t e;
+    if (c_dev != p.device || c_C != cc.C || c_smem != cc.smem) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            const int d = p.device & 63;
+            if (cc.smem > smem_set[d]) {
+                e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem);
+                if (e != cudaSuccess) return e;
+                smem_set[d] = cc.smem;
+            }
+            if (cc.C > 8 && !nonportable_set[d]) {
+                e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                if (e != cudaSuccess) return e;
+                nonportable_set[d] = true;
+            }
+        }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+        cfg.gridDim = dim3((unsigned)(sms / cc.C * cc.C));
+        int q = 0;
+        e = cudaOccupancyMaxActiveClusters(&q, kernel, &cfg);
+        if (e != cudaSuccess) return e;
+        if (q < 1) return cudaErrorLaunchOutOfResources;
+        c_dev = p.device; c_C = cc.C; c_smem = cc.smem; c_max = q;
+    }
+    const int max_clusters = c_max;
     if (wave_only != nullptr) { *wave_only = max_clusters; return cudaSuccess; }
     const int ncl = max_clusters < a.nshots ? max_clusters : a.nshots;
     cfg.gridDim = dim3((unsigned)(ncl * cc.C));
