@@ -342,7 +342,7 @@ def main():
         n = {k: kernel_n[k] // args.steps for k in kernel_n}
         cell_updates = float(cells_level) * nt
         kernels = {
-            "forward": {"kernel": "k_fwd_cluster<EXACT>" if fwd_cluster else "k_fwd_step", "us": us["forward"],
+            "forward": {"kernel": "k_fwd_cluster<EXACT>" if fwd_cluster else "k_step_tile<EXACT>", "us": us["forward"],
                         "launches": n["forward"] if fwd_cluster else launches_f - 3,
                         # recompute tier: the forward kernel really runs twice per step (modelling + per-chunk recompute)
                         "algo_bytes": ALGO_BYTES_FWD * cell_updates * (2 if recompute else 1)},
@@ -351,8 +351,9 @@ def main():
             # the adjoint's 16 B / cell-update split as: adjoint-field kernel (read u_{t+1}, u_{t+2}, write u_t = 12 B; all of
             # it stays in shared memory, only the 4 B history write reaches HBM) + imaging kernel (pointwise: read p_t and
             # u_t once each = 8 B, which is exactly what it streams from HBM)
-            kernels["adjoint_field"] = {"kernel": "k_fwd_cluster<ADJ>", "us": us["adjoint_field"], "launches": n["adjoint_field"],
-                                        "algo_bytes": 12.0 * cell_updates}
+            tiled = plan.get("adj_split") == 3   # per-level engine: nt tiled launches per chunk of shots
+            kernels["adjoint_field"] = {"kernel": "k_step_tile<ADJ>" if tiled else "k_fwd_cluster<ADJ>", "us": us["adjoint_field"],
+                                        "launches": n["adjoint_field"] * (nt if tiled else 1), "algo_bytes": 12.0 * cell_updates}
             kernels["imaging"] = {"kernel": "k_imaging", "us": us["imaging"], "launches": n["imaging"],
                                   "algo_bytes": 8.0 * cell_updates}
         else:
@@ -381,7 +382,8 @@ def main():
                        "history": ("none kept: forward field recomputed per chunk of %d shots in the backward pass" % plan.get("u_chunk_used")) if recompute
                                   else (("checkpoint pairs every %d levels" % seg) if seg else "every level"),
                        "engine": {"forward": "cluster-resident (C=%d)" % plan.get("cluster_size_used") if fwd_cluster else "per-level",
-                                  "adjoint": ("split: cluster-resident adjoint field (C=%d) + streaming imaging" % plan.get("cluster_size_used")) if adj_split
+                                  "adjoint": ("split: per-level tiled adjoint field + streaming imaging" if plan.get("adj_split") == 3 else
+                                              "split: cluster-resident adjoint field (C=%d) + streaming imaging" % plan.get("cluster_size_used")) if adj_split
                                   else ("cluster-resident fused (C=%d)" % plan.get("adj_cluster_size_used") if adj_cluster else "per-level")},
                        "options": dict(op.options)},
             "e2e": {"value": e2e_value, "unit": "pairs/s",

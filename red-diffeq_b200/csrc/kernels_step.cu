@@ -1,11 +1,6 @@
-// kernels_step.cu -- one time level of the forward recurrence and of its adjoint, all shots of a chunk.
-//
-// Forward (replaces the body of the hot loop, solvers/pde.py:79-83, ~48 ATen launches per level):
-//     p = temp1*p1 - temp2*p0 + alpha*(c2*(4 rolls by +-1) + c3*(4 rolls by +-2))     (:79)
-//     p[src] += beta_dt[src] * wavelet[t]                                              (:80-81)
-//     seis[t/st] = p[igz, igx]   (sampled after injection)                             (:82-83)
-//   fp32, one rounding per reference tensor op, in the reference's association order
-//   (__fmul_rn/__fadd_rn/__fsub_rn: ptxas may not contract them into FMAs) => bit-identical seismograms.
+// kernels_step.cu -- one time level of the FUSED per-level adjoint (q-variable, imaging sums accumulated in place), all
+// shots of a chunk.  Used with histories checkpointed in time and with option adj_mode = 1; the default per-level
+// adjoint is the split one (kernels_tile.cu in adjoint-field mode + kernels_imaging.cu).
 //
 // Adjoint (replaces what autograd replays from the tape, core/inversion.py:86):
 //     q_t  = T1 q_{t+1} + S(alpha q_{t+1}) - T2 q_{t+2}  (+ receiver cotangent of level t)
@@ -60,99 +55,6 @@ __device__ __forceinline__ void load_kappa(const float *__restrict__ kap_b, cons
         const int kx = sponge_index(c.xc[j], g.nxp, g.nbc);
         const int k = kx >= 0 ? kx : (kz >= 0 ? kz : g.nbc);
         kp[j] = kap_b[k];
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ forward
-template <int R>
-__global__ void __launch_bounds__(kThreads) k_fwd_step(FwdArgs a, Grid g)
-{
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    const int ngroups = (g.nzp + R - 1) / R;
-    if (i >= ngroups * g.q4) return;
-    const int zg = i / g.q4;
-    const int x = (i - zg * g.q4) * 4;
-    const int z0 = zg * R;
-    const int b = blockIdx.y;
-    const Cols c = make_cols(x, g.nxp);
-
-    // offsets of rows z0-2 .. z0+R+1 (periodic in z)
-    int roff[R + 4];
-#pragma unroll
-    for (int k = 0; k < R + 4; ++k) {
-        int z = z0 - 2 + k;
-        z = z < 0 ? z + g.nzp : (z >= g.nzp ? z - g.nzp : z);
-        roff[k] = z * g.pitch;
-    }
-
-    // per-cell coefficients, shared by all shots of the model
-    float al[R][4], kp[R][4];
-    const float *alpha_b = a.alpha + (size_t)b * g.level;
-    const float *kap_b = a.kap + (size_t)b * (g.nbc + 1);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float4 v = ld4(alpha_b + roff[r + 2] + x);
-        al[r][0] = v.x; al[r][1] = v.y; al[r][2] = v.z; al[r][3] = v.w;
-        load_kappa(kap_b, c, z0 + r, g, kp[r]);
-    }
-
-    const float c2 = 4.0f / 3.0f;    // fp32(4.0/3.0), the reference's python scalar cast by the tensor op
-    const float c3 = -1.0f / 12.0f;
-
-    for (int s = blockIdx.z; s < g.ns; s += gridDim.z) {  // shots are dealt over grid.z when the grid would not fill the GPU
-        const size_t shot = (size_t)(b * g.ns + s);
-        const float *__restrict__ P1 = a.p1 + shot * a.ss_p1;
-        const float *__restrict__ P0 = a.p0 + shot * a.ss_p0;
-        float *__restrict__ PO = a.out + shot * a.ss_out;
-
-        float4 rows[R + 4];
-#pragma unroll
-        for (int k = 0; k < R + 4; ++k) rows[k] = ld4(P1 + roff[k] + x);
-        float4 old[R];
-        float sc[R][4];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            old[r] = ld4(P0 + roff[r + 2] + x);
-            sc[r][0] = P1[roff[r + 2] + c.xm2];
-            sc[r][1] = P1[roff[r + 2] + c.xm1];
-            sc[r][2] = P1[roff[r + 2] + c.xp4];
-            sc[r][3] = P1[roff[r + 2] + c.xp5];
-        }
-        const int xs = a.isx[s];
-        const float src_add = __fmul_rn(a.beta_src[b * g.ns + s], a.w_t);
-
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int z = z0 + r;
-            if (z < g.nzp) {
-                const float e[8] = {sc[r][0], sc[r][1], rows[r + 2].x, rows[r + 2].y, rows[r + 2].z, rows[r + 2].w,
-                                    sc[r][2], sc[r][3]};
-                float o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    // (((p1[z-1] + p1[z+1]) + p1[x-1]) + p1[x+1]) and the same at distance 2   (:79)
-                    const float s1 = __fadd_rn(__fadd_rn(__fadd_rn(lane(rows[r + 1], j), lane(rows[r + 3], j)), e[j + 1]), e[j + 3]);
-                    const float s2 = __fadd_rn(__fadd_rn(__fadd_rn(lane(rows[r], j), lane(rows[r + 4], j)), e[j]), e[j + 4]);
-                    const float lap = __fadd_rn(__fmul_rn(c2, s1), __fmul_rn(c3, s2));
-                    const float t1 = __fsub_rn(__fadd_rn(2.0f, __fmul_rn(-5.0f, al[r][j])), kp[r][j]);  // temp1 (:69)
-                    const float t2 = __fsub_rn(1.0f, kp[r][j]);                                         // temp2 (:70)
-                    float val = __fadd_rn(__fsub_rn(__fmul_rn(t1, e[j + 2]), __fmul_rn(t2, lane(old[r], j))),
-                                          __fmul_rn(al[r][j], lap));
-                    if (z == g.isz && c.xc[j] == xs) val = __fadd_rn(val, src_add);  // (:81)
-                    o[j] = val;
-                }
-                st4(PO + roff[r + 2] + x, make_float4(o[0], o[1], o[2], o[3]));
-                if (a.seis != nullptr && z == g.igz) {
-                    float *d = a.seis + ((size_t)(b * g.ns + s) * g.nt_out + a.it_out) * g.nrec;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (x + j < g.nxp) {
-                            for (int k = a.rec_ptr[x + j]; k < a.rec_ptr[x + j + 1]; ++k) d[a.rec_idx[k]] = o[j];
-                        }
-                    }
-                }
-            }
-        }
     }
 }
 
@@ -316,22 +218,6 @@ int adj_shot_slices(const Plan &p, int nb)
     const int R = p.adj_rows_per_thread;
     const int groups = (g.nzp + R - 1) / R;
     return shot_slices(p, (groups * g.q4 + kThreads - 1) / kThreads, nb, 4);
-}
-
-cudaError_t launch_fwd_step(const Plan &p, const FwdArgs &a, int nb, cudaStream_t st)
-{
-    const Grid &g = p.g;
-    const int R = p.rows_per_thread;
-    const int groups = (g.nzp + R - 1) / R;
-    const int bxy = (groups * g.q4 + kThreads - 1) / kThreads;
-    const dim3 grid((unsigned)bxy, (unsigned)nb, (unsigned)shot_slices(p, bxy, nb, 1));
-    switch (R) {
-        case 1: k_fwd_step<1><<<grid, kThreads, 0, st>>>(a, g); break;
-        case 2: k_fwd_step<2><<<grid, kThreads, 0, st>>>(a, g); break;
-        default: k_fwd_step<4><<<grid, kThreads, 0, st>>>(a, g); break;
-    }
-    count_launch();
-    return cudaSuccess;
 }
 
 cudaError_t launch_adj_step(const Plan &p, const AdjArgs &a, int nb, cudaStream_t st)

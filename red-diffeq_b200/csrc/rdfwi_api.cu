@@ -112,6 +112,7 @@ struct Workspace {
     float *seg_hist = nullptr;
     bool split = false;
     bool fused = false;       // fused cluster-resident adjoint (k_adj_cluster) when the split adjoint is not used
+    bool split_tile = false;  // split adjoint on the per-level engine: tiled adjoint-field levels + streaming imaging
     bool recompute = false;   // split adjoint on a forward history recomputed chunk by chunk (history_segment >= nt)
     int u_chunk = 0;
     float *u_hist = nullptr;
@@ -176,8 +177,20 @@ Workspace carve(const Plan &p, int B, void *base)
         if (p.u_chunk_shots == 0 && !single_segment && w.u_chunk < nshots && w.u_chunk < wave && fused_ok) { w.split = false; w.u_chunk = 0; }
     }
     w.fused = fused_ok && !w.split;
+    // per-level engine, every level kept: the adjoint is split too (tiled adjoint-field levels into a scratch history of a
+    // chunk of shots, then the pointwise imaging kernel); adj_mode = 1 keeps the fused per-level adjoint
+    w.split_tile = !w.split && !w.fused && p.history_segment == 0 && p.adj_mode == 0;
+    if (w.split_tile) {
+        const int nshots = B * g.ns;
+        const double per_shot = (double)p.nt * (double)g.level * sizeof(float);
+        const double cap = p.scratch_mb > 0 ? 1e6 * (double)p.scratch_mb : 40e9;
+        int chunk = p.u_chunk_shots > 0 ? p.u_chunk_shots : std::max(1, (int)(cap / per_shot));
+        chunk = std::min(chunk, nshots);
+        const int nchunks = (nshots + chunk - 1) / chunk;
+        w.u_chunk = (nshots + nchunks - 1) / nchunks;
+    }
     // imaging planes per model: one per shot for the cluster engines, one per grid.z slice for the per-level adjoint
-    w.g_planes = (w.split || fused_ok) ? g.ns : adj_shot_slices(p, w.nb);
+    w.g_planes = (w.split || fused_ok || w.split_tile) ? g.ns : adj_shot_slices(p, w.nb);
     w.Ga = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gk = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gb = (float *)take((size_t)B * g.ns * 4);
@@ -186,7 +199,7 @@ Workspace carve(const Plan &p, int B, void *base)
     // checkpoint mode: the levels of one segment of one chunk, recomputed during the backward pass
     w.seg_hist = (p.history_segment > 0 && !w.recompute) ? (float *)take(w.chunk_level * (size_t)(p.history_segment - 1) * 4) : nullptr;
     // split adjoint: adjoint-field history of one chunk of shots (+ the recomputed forward history of the chunk)
-    if (w.split) w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
+    if (w.split || w.split_tile) w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
     if (w.recompute) w.p_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
     w.bytes = off;
     return w;
@@ -332,7 +345,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     Plan *p = reinterpret_cast<Plan *>(plan);
     const std::string k(key);
     if (k == "chunk_models") { if (value < 0) goto bad; p->chunk_models = (int)value; }
-    else if (k == "rows_per_thread") { if (value != 1 && value != 2 && value != 4) goto bad; p->rows_per_thread = (int)value; }
+    else if (k == "rows_per_thread") { if (value != 1 && value != 2 && value != 4 && value != 8) goto bad; p->rows_per_thread = (int)value; }
     else if (k == "adj_rows_per_thread") { if (value != 1 && value != 2) goto bad; p->adj_rows_per_thread = (int)value; }
     else if (k == "engine") { if (value < 0 || value > 2) goto bad; p->engine = (int)value; }
     else if (k == "history_segment") { if (value < 0 || value == 1 || value == 2) goto bad; p->history_segment = (int)value; }
@@ -484,18 +497,17 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
             return w.fields + (size_t)((t + 3) % 3) * w.chunk_level;
         };
         for (int t = 0; t < nt; ++t) {
-            FwdArgs a;
+            StepArgs a{};
             a.p1 = level_ptr(t - 1, &a.ss_p1);
             a.p0 = level_ptr(t - 2, &a.ss_p0);
             a.out = level_ptr(t, &a.ss_out);
-            a.alpha = w.alpha + (size_t)b0 * g.level;
-            a.kap = w.kap + (size_t)b0 * (g.nbc + 1);
-            a.beta_src = w.beta_src + (size_t)b0 * g.ns;
+            a.alpha = w.alpha; a.kap = w.kap; a.beta_src = w.beta_src;
             a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
-            a.seis = (t % p.st == 0) ? seis + (size_t)b0 * g.ns * g.nt_out * g.nrec : nullptr;
+            a.seis = (t % p.st == 0) ? seis : nullptr;
             a.it_out = t / p.st;
             a.w_t = p.wavelet[t];
-            launch_fwd_step(p, a, nb, st);
+            a.shot0 = b0 * g.ns; a.nshots = nb * g.ns;
+            launch_step_tile(p, a, st);
         }
     }
     RD_CUDA(cudaGetLastError());
@@ -567,6 +579,39 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     }
     if (p.engine == 2 && !ckpt) { set_error("engine=2 (cluster-resident) requested but the adjoint slabs do not fit a cluster"); return RDFWI_EINVAL; }
     RD_CUDA(cudaMemsetAsync(w.zero, 0, w.chunk_level * sizeof(float), st));
+    if (!ckpt && w.split_tile) {
+        // split adjoint on the per-level engine: per chunk of shots, nt tiled launches write the adjoint field u_t (slot k
+        // of the scratch history = reverse level nt-1-k), then the imaging kernel streams both histories once
+        const_cast<Plan &>(p).last_split = 3;
+        const_cast<Plan &>(p).last_u_chunk = w.u_chunk;
+        const int nshots = B * g.ns;
+        const unsigned long long ustride = (unsigned long long)nt * g.level;
+        for (int s0 = 0; s0 < nshots; s0 += w.u_chunk) {
+            const int n = std::min(w.u_chunk, nshots - s0);
+            {
+                Timed timed(p, 1, st);
+                for (int k = 0; k < nt; ++k) {
+                    const int t = nt - 1 - k;
+                    StepArgs a{};
+                    a.p1 = k >= 1 ? w.u_hist + (size_t)(k - 1) * g.level : w.zero; a.ss_p1 = k >= 1 ? ustride : 0;
+                    a.p0 = k >= 2 ? w.u_hist + (size_t)(k - 2) * g.level : w.zero; a.ss_p0 = k >= 2 ? ustride : 0;
+                    a.out = w.u_hist + (size_t)k * g.level; a.ss_out = ustride;
+                    a.alpha = w.alpha; a.kap = w.kap; a.beta_src = w.beta_src;
+                    a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
+                    a.cot = (t % p.st == 0) ? cot : nullptr;
+                    a.it_out = t / p.st;
+                    a.w_t = p.wavelet[t];
+                    a.Gb = w.Gb;
+                    a.shot0 = s0; a.nshots = n; a.adj = 1; a.last = k == nt - 1;
+                    launch_step_tile(p, a, st);
+                }
+            }
+            Timed timed(p, 2, st);
+            RD_CUDA(launch_imaging(p, hist, w.u_hist, w.alpha, w.kap, w.beta_src, w.Gb, w.Ga, w.Gk, s0, n, 0, st));
+        }
+        RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
+        return RDFWI_OK;
+    }
     const int K = segment;
     const int nseg = ckpt ? num_segments(p, K) : 1;
     const size_t ck_stride = ckpt ? (size_t)(nseg - 1) * 2 * g.level : 0;
@@ -600,17 +645,16 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
             if (ckpt) {
                 // recompute p_{t0} .. p_{t1-2} from the checkpoint pair (zeros for the first segment)
                 for (int t = t0; t <= t1 - 2; ++t) {
-                    FwdArgs f;
+                    StepArgs f{};
                     f.p1 = forward_level(t - 1, t0, &f.ss_p1);
                     f.p0 = forward_level(t - 2, t0, &f.ss_p0);
                     f.out = const_cast<float *>(forward_level(t, t0, &f.ss_out));
-                    f.alpha = w.alpha + (size_t)b0 * g.level;
-                    f.kap = w.kap + (size_t)b0 * (g.nbc + 1);
-                    f.beta_src = w.beta_src + (size_t)b0 * g.ns;
+                    f.alpha = w.alpha; f.kap = w.kap; f.beta_src = w.beta_src;
                     f.isx = p.d_isx; f.rec_ptr = p.d_rec_ptr; f.rec_idx = p.d_rec_idx;
                     f.seis = nullptr; f.it_out = 0;
                     f.w_t = p.wavelet[t];
-                    launch_fwd_step(p, f, nb, st);
+                    f.shot0 = b0 * g.ns; f.nshots = nb * g.ns;
+                    launch_step_tile(p, f, st);
                 }
             }
             for (int t = t1 - 1; t >= t0; --t) {

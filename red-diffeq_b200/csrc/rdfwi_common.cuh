@@ -56,7 +56,7 @@ struct Plan {
     float *d_wavelet = nullptr;  // (nt) fp32 wavelet for the cluster-resident kernels
     // options
     int chunk_models = 0;   // 0 = auto
-    int rows_per_thread = 2;
+    int rows_per_thread = 4;
     int adj_rows_per_thread = 1;
     int engine = 0;         // 0 = auto, 1 = per-level kernels, 2 = cluster-resident time loop
     int cluster_size = 0;   // 0 = smallest cluster that fits
@@ -126,21 +126,25 @@ struct ClusterConfig {
     int nthreads = 512;     // threads per CTA
 };
 
-// Pointers of one step launch (forward).
-struct FwdArgs {
-    const float *p1;        // level t-1 of the chunk
-    const float *p0;        // level t-2
+// One time level of the tiled per-level kernel (kernels_tile.cu): forward field, or adjoint field in the u-variable.
+struct StepArgs {
+    const float *p1;        // level t-1 (adjoint: u_{t+1}) of the launch's first shot
+    const float *p0;        // level t-2 (adjoint: u_{t+2})
     float *out;             // level t
-    const float *alpha;     // (nb, nzp, pitch)
-    const float *kap;       // (nb, nbc+1)
-    const float *beta_src;  // (nb, ns)
+    unsigned long long ss_p1, ss_p0, ss_out;  // floats between consecutive shots in p1 / p0 / out (0 = one shared zero level)
+    const float *alpha;     // (B, nzp, pitch)   whole batch: indexed by the global model of a shot
+    const float *kap;       // (B, nbc+1)
+    const float *beta_src;  // (B*ns)
     const int *isx;
     const int *rec_ptr;
     const int *rec_idx;
-    float *seis;            // (nb, ns, nt_out, nrec) or nullptr when this level is not sampled
+    float *seis;            // forward: (B*ns, nt_out, nrec) or nullptr when this level is not sampled
+    const float *cot;       // adjoint: (B*ns, nt_out, nrec) or nullptr when this level carries no cotangent
+    float *Gb;              // adjoint: (B*ns) running sum_t u_t[src] w_t; divided by alpha_src at the last level
     int it_out;
     float w_t;
-    unsigned long long ss_p1, ss_p0, ss_out;  // floats between consecutive shots in p1 / p0 / out
+    int shot0, nshots;      // global index of the launch's first shot, shots in the launch (grid.z)
+    int adj, last;          // adjoint-field mode; last level of the reverse loop (t = 0)
 };
 
 struct AdjArgs {
@@ -169,8 +173,9 @@ void count_launch();
 // kernels_prologue.cu
 cudaError_t launch_coefficients(const Plan &p, const float *v, int B, float *alpha_pad, float *kap, float *velmin,
                                 int *argmin, float *beta_src, float *minpart, cudaStream_t st);
+// kernels_tile.cu
+cudaError_t launch_step_tile(const Plan &p, const StepArgs &a, cudaStream_t st);
 // kernels_step.cu
-cudaError_t launch_fwd_step(const Plan &p, const FwdArgs &a, int nb, cudaStream_t st);
 cudaError_t launch_adj_step(const Plan &p, const AdjArgs &a, int nb, cudaStream_t st);
 int adj_shot_slices(const Plan &p, int nb);  // imaging planes per model the per-level adjoint accumulates into
 // kernels_cluster.cu

@@ -211,6 +211,8 @@ class FWIForward(nn.Module):
                 if "u_chunk_shots" not in user:
                     tiers.append((plan.nt, {"u_chunk_shots": wave}))
                 tiers += [(0, {}), (0, {"adj_mode": 1})]
+            elif "adj_mode" not in user:
+                tiers.append((0, {"adj_mode": 1}))   # per-level engine: the fused adjoint needs no scratch history
             seg, extra = max(3, int(np.ceil(np.sqrt(2.0 * plan.nt)))), {}   # minimises pairs + segment levels
             for cand_seg, cand_extra in tiers:
                 if fits(cand_seg, **cand_extra):

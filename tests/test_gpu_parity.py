@@ -59,20 +59,22 @@ def test_gradient_matches_reference(golden):
 
 
 @pytest.mark.parametrize("name", ["tiny_default", "tiny_custom", "tiny_half_receivers"])
-@pytest.mark.parametrize("rows", [1, 2, 4])
+@pytest.mark.parametrize("rows", [1, 2, 4, 8])
 @pytest.mark.parametrize("chunk", [0, 1])
-@pytest.mark.parametrize("engine", ["per-level", "cluster-split", "cluster-fused"])
+@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "cluster-split", "cluster-fused"])
 def test_kernel_variants_agree_with_oracle(name, rows, chunk, engine, oracle):
-    if engine != "per-level" and (rows != 1 or chunk != 0):
+    if not engine.startswith("per-level") and (rows != 1 or chunk != 0):
         pytest.skip("rows/chunk only affect the per-level engine")
     g = Golden(name)
     op = _op(g)
-    op.set_option("engine", 1 if engine == "per-level" else 2)
-    op.set_option("adj_mode", 1 if engine == "cluster-fused" else 0)   # split (default) or fused cluster adjoint
+    op.set_option("engine", 1 if engine.startswith("per-level") else 2)
+    op.set_option("adj_mode", 1 if engine.endswith("fused") else 0)   # split (default) or fused adjoint
+    if engine == "per-level":
+        op.set_option("u_chunk_shots", 3)                                 # several chunks even on the tiny cases
     if engine == "cluster-split":
         op.set_option("u_chunk_shots", 2)                                 # several chunks even on the tiny cases
     op.set_option("rows_per_thread", rows)
-    op.set_option("adj_rows_per_thread", 1 if rows == 1 else 2)
+    op.set_option("adj_rows_per_thread", 1 if rows in (1, 8) else 2)
     op.set_option("chunk_models", chunk)
     sv = oracle.Survey(g.fresh_ctx(), g.v.shape[2], g.v.shape[3], g.sample_temporal, g.sample_spatial)
     cot = g.cotangent((g.v.shape[0], sv.ns, sv.nt_out, sv.nrec))
@@ -90,6 +92,7 @@ def test_checkpointed_history_matches_full_history(name, segment):
     g = Golden(name)
     full = _op(g)
     full.set_option("engine", 1)
+    full.set_option("adj_mode", 1)   # the fused per-level adjoint: the kernel the checkpointed path runs
     full.set_history_segment(0)
     ck = _op(g)
     ck.set_option("engine", 1)     # (segment >= nt on the cluster engine is the recompute tier, tested below)
@@ -128,7 +131,7 @@ def test_recomputed_history_matches_full_history(name, chunk):
     assert rel_l2(g1, g.grad_f32) <= GRAD_TOL
 
 
-@pytest.mark.parametrize("engine", ["per-level", "per-level-checkpointed", "cluster-split", "cluster-fused"])
+@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "per-level-checkpointed", "cluster-split", "cluster-fused"])
 def test_many_shots_per_model(engine, oracle):
     """More shots than any golden case (ns = 11: the per-level adjoint deals them over several grid.z slices, each with its
     own imaging plane; the cluster engines run more shots than fit one chunk)."""
@@ -141,8 +144,8 @@ def test_many_shots_per_model(engine, oracle):
     cot = synthetic.cotangent((B, sv.ns, sv.nt_out, sv.nrec), seed=32)
     op = FWIForward(dict(ctx), "cuda:0", normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
     op.set_option("engine", 1 if engine.startswith("per-level") else 2)
-    op.set_option("adj_mode", 1 if engine == "cluster-fused" else 0)
-    if engine == "cluster-split":
+    op.set_option("adj_mode", 1 if engine.endswith("fused") else 0)
+    if engine in ("cluster-split", "per-level"):
         op.set_option("u_chunk_shots", 7)
     if engine == "per-level-checkpointed":
         op.set_history_segment(16)
@@ -271,7 +274,7 @@ def test_errors():
 
 
 @pytest.mark.parametrize("nx,nbc", [(15, 9), (17, 9), (21, 10), (16, 8)])
-@pytest.mark.parametrize("engine", ["per-level", "cluster-split", "cluster-fused"])
+@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "cluster-split", "cluster-fused"])
 def test_odd_widths_against_oracle(nx, nbc, engine, oracle):
     """Padded widths with nxp % 4 in {1, 3, 0, ...}: the periodic image columns of the pitched layout (1..3 of them)
     must reproduce torch.roll's wrap-around bit for bit; no reference fixture has such a width, so the pinned oracle checks."""
@@ -281,8 +284,8 @@ def test_odd_widths_against_oracle(nx, nbc, engine, oracle):
     rng = np.random.default_rng(nx * 100 + nbc)
     v = (1500 + 3000 * rng.random((2, 1, nz, nx))).astype(np.float32)
     op = FWIForward(dict(ctx), "cuda:0", normalize=False)
-    op.set_option("engine", 1 if engine == "per-level" else 2)
-    op.set_option("adj_mode", 1 if engine == "cluster-fused" else 0)
+    op.set_option("engine", 1 if engine.startswith("per-level") else 2)
+    op.set_option("adj_mode", 1 if engine.endswith("fused") else 0)
     sv = oracle.Survey(dict(ctx), nz, nx)
     cot = rng.standard_normal((2, sv.ns, sv.nt_out, sv.nrec)).astype(np.float32)
     seis, grad = _run(op, v, cot)
@@ -290,6 +293,27 @@ def test_odd_widths_against_oracle(nx, nbc, engine, oracle):
     assert (sv.nxp % 4) == (nx + 2 * nbc) % 4
     assert np.array_equal(seis, seis_o)
     assert rel_l2(grad, grad_o) <= GRAD_TOL
+
+
+def test_tiled_engine_on_a_grid_wider_than_a_tile(oracle):
+    """Per-level engine on a grid of several 128-column x 32-row tiles (padded 172 x 330, width not a multiple of 4 or
+    128; the engine is forced, this size would fit a cluster): bit-identical seismograms, gradient against the pinned oracle."""
+    from red_diffeq_b200 import FWIForward
+    nz, nx, nbc = 132, 290, 20
+    ctx = dict(n_grid=nx, nt=140, dx=10.0, dt=0.001, nbc=nbc, f=25.0, sz=15, gz=12, ng=nx, ns=3)
+    rng = np.random.default_rng(77)
+    v = (1500 + 3000 * rng.random((1, 1, nz, nx))).astype(np.float32)
+    sv = oracle.Survey(dict(ctx), nz, nx)
+    cot = rng.standard_normal((1, sv.ns, sv.nt_out, sv.nrec)).astype(np.float32)
+    seis_o, grad_o = oracle.gradient(sv, v, cot)
+    for rows in (4, 8):
+        op = FWIForward(dict(ctx), "cuda:0", normalize=False)
+        op.set_option("engine", 1)
+        op.set_option("rows_per_thread", rows)
+        op.set_option("u_chunk_shots", 2)
+        seis, grad = _run(op, v, cot)
+        assert np.array_equal(seis, seis_o)
+        assert rel_l2(grad, grad_o) <= GRAD_TOL
 
 
 def test_full_size_batch_properties():

@@ -18,6 +18,7 @@ sys.path.insert(0, ROOT)
 from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize  # noqa: E402
 from red_diffeq_b200.utils import synthetic  # noqa: E402
 
+OPTS = {}
 CASES = [  # (n, ns, B, nt)
     (70, 5, 1, 1000), (70, 5, 64, 1000), (128, 1, 1, 1000), (128, 16, 1, 1000), (128, 64, 1, 1000), (128, 256, 1, 1000),
     (256, 16, 1, 1000), (256, 64, 1, 1000), (512, 4, 1, 1000), (512, 16, 1, 1000), (512, 64, 1, 1000),
@@ -28,6 +29,8 @@ CASES = [  # (n, ns, B, nt)
 def run_case(n, ns, B, nt, peak):
     ctx = dict(n_grid=n, nt=nt, dx=10.0, dt=0.001, nbc=120, f=15.0, sz=10, gz=10, ng=n, ns=ns)
     op = FWIForward(ctx, "cuda:0", normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    for k, val in OPTS.items():
+        op.set_option(k, val)
     v = torch.tensor(synthetic.velocity_models(B, n, n), device="cuda:0")
     plan = op._plan_for(n, n, torch.device("cuda:0"))
 
@@ -47,7 +50,9 @@ def run_case(n, ns, B, nt, peak):
     rate = pairs / ((f_ms + a_ms) * 1e-3)
     seg = plan.get("history_segment")
     eng_f = "cluster C=%d" % plan.get("cluster_size_used") if plan.get("cluster_size_used") and not seg else "per-level"
-    eng_a = ("split" if plan.get("adj_split") else "cluster C=%d" % plan.get("adj_cluster_size_used")) if (plan.get("adj_split") or plan.get("adj_cluster_size_used")) and not seg else "per-level"
+    sp = plan.get("adj_split")
+    eng_a = {1: "cluster split", 2: "cluster split, forward recomputed", 3: "per-level split"}.get(sp) or \
+        (("cluster fused C=%d" % plan.get("adj_cluster_size_used")) if plan.get("adj_cluster_size_used") and not seg else "per-level fused")
     op.release_memory()
     return dict(n=n, ns=ns, B=B, nt=nt, forward_ms=f_ms, adjoint_ms=a_ms, pairs_per_s=rate, frac=rate * 28 / (peak * 1e9),
                 engine_fwd=eng_f, engine_adj=eng_a, history="checkpoint K=%d" % seg if seg else "full")
@@ -57,10 +62,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--min-n", type=int, default=0, help="only cases with interior n >= this")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value")
     args = ap.parse_args()
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     rows = []
-    for case in (CASES[:4] if args.quick else CASES):
+    global OPTS
+    OPTS = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in args.opt)
+    for case in (CASES[:4] if args.quick else [c for c in CASES if c[0] >= args.min_n]):
         try:
             rows.append(run_case(*case, peak))
         except Exception as ex:  # report and continue
