@@ -63,13 +63,22 @@ int rdfwi_plan_create(const rdfwi_survey *survey, rdfwi_plan *plan_out);
 int rdfwi_plan_destroy(rdfwi_plan plan);
 
 /* Tunables (all optional).  Keys:
- *   "chunk_models"   models advanced together through the time loop (0 = auto: sized for L2)
- *   "rows_per_thread" / "adj_rows_per_thread"  z-rows marched per thread in the per-level step kernels
- *   "engine"         0 = by problem size (default), 1 = per-level kernels, 2 = cluster-resident time loop
- *   "cluster_size" / "adj_cluster_size"  CTAs per cluster of the cluster-resident kernels (0 = smallest that fits)
- *   "history_segment" 0 = keep every level, K >= 3 = checkpoint pairs every K levels (must be set BEFORE the
- *                    workspace / history sizes are queried; forward/backward's `segment` must equal it)
- * rdfwi_plan_get additionally answers "pitch", "nzp", "nxp", "nt_out", "cluster_size_used", "adj_cluster_size_used". */
+ *   "engine"         0 = by problem size (default), 1 = per-level tiled kernels, 2 = cluster-resident time loop
+ *   "adj_mode"       0 = split adjoint (adjoint-field kernel + streaming imaging kernel; default), 1 = fused adjoint
+ *   "history_segment" 0 = keep every level; K >= 3 = keep a pair of levels every K levels and recompute K levels at a
+ *                    time in the backward pass; K >= nt = keep nothing, the backward pass recomputes the forward field
+ *                    chunk by chunk (must be set BEFORE the workspace / history sizes are queried; the `segment`
+ *                    argument of forward/backward must equal it)
+ *   "u_chunk_shots"  shots per chunk of the split adjoint (0 = auto: whole waves of co-resident clusters)
+ *   "scratch_mb"     cap on one scratch history of the split adjoint, MB (0 = 40000; 55000 for the recompute tier)
+ *   "cluster_size" / "adj_cluster_size"  CTAs per cluster of the cluster-resident kernels (0 = smallest of 1..8 that fits)
+ *   "rows_per_thread" (1, 2, 4, 8; tile rows = 8x) / "adj_rows_per_thread"  z-rows marched per thread, per-level kernels
+ *   "chunk_models"   models advanced together by the per-level forward (0 = auto)
+ *   "timing"         1 = record CUDA events around each kernel class on the caller's stream (read back as "us_<class>",
+ *                    "n_<class>" with class in forward, adjoint_field, imaging, adjoint_loop)
+ * rdfwi_plan_get additionally answers "pitch", "nzp", "nxp", "nt_out", "cluster_size_used", "adj_cluster_size_used",
+ * "cluster_wave" (co-resident clusters of the forward configuration), "adj_split" (what the last backward ran: 0 fused,
+ * 1 cluster split, 2 cluster split on a recomputed forward history, 3 per-level split), "u_chunk_used". */
 int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value);
 int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *value_out);
 
@@ -83,7 +92,8 @@ size_t rdfwi_workspace_bytes(rdfwi_plan plan, int32_t B);
  *   segment == 0 : every level is kept (B*ns*nt levels)
  *   segment == K : the pair (p_{jK-2}, p_{jK-1}) in front of every segment j >= 1 of K levels is kept; the backward
  *                  pass recomputes one segment at a time into the workspace (one extra forward, memory / (K/2)).
- *                  May be 0 bytes (single segment): a NULL history is then accepted by rdfwi_backward. */
+ *                  0 bytes when K >= nt (single segment: nothing is kept, the backward pass recomputes the forward
+ *                  field from the zero initial state); a NULL history is then accepted by forward and backward. */
 size_t rdfwi_history_bytes(rdfwi_plan plan, int32_t B, int32_t segment);
 
 /*

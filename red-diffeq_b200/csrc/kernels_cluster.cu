@@ -407,6 +407,9 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg)
     if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device) != cudaSuccess) return false;
     for (int C = 1; C <= 16; ++C) {
         if (C > 8 && C != 16) continue;  // 1..8 are portable cluster sizes, 16 needs the non-portable opt-in
+        // 16-CTA clusters (31-row slabs, 8 co-resident clusters) lose to the tiled per-level engine on the grids that
+        // need them (interior 256^2: 1.25e11 vs 1.02e11 pairs/s at 16 shots, profiles/sweep_r1.md): only on request
+        if (C == 16 && p.cluster_size != 16 && p.engine != 2) continue;
         if (p.cluster_size > 0 && C != p.cluster_size) continue;
         if (g.nzp / C < 2) break;
         const int maxrows = (g.nzp + C - 1) / C;

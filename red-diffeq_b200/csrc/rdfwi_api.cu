@@ -153,7 +153,7 @@ Workspace carve(const Plan &p, int B, void *base)
     // (a single segment: nothing is kept) runs the split adjoint on a forward history recomputed chunk by chunk.
     const bool single_segment = p.history_segment >= p.nt;
     const bool cluster_ok = p.engine != 1 && (p.history_segment == 0 || single_segment);
-    const bool fused_ok = cluster_ok && !single_segment && adj_cluster_config(p, &acc);
+    const bool fused_ok = cluster_ok && !single_segment && cluster_config(p, &fcc) && adj_cluster_config(p, &acc);  // (cluster forward too)
     w.split = cluster_ok && (p.adj_mode == 0 || single_segment) && cluster_config(p, &fcc);
     w.recompute = w.split && single_segment;
     w.u_chunk = 0;

@@ -212,7 +212,17 @@ class FWIForward(nn.Module):
                     tiers.append((plan.nt, {"u_chunk_shots": wave}))
                 tiers += [(0, {}), (0, {"adj_mode": 1})]
             elif "adj_mode" not in user:
-                tiers.append((0, {"adj_mode": 1}))   # per-level engine: the fused adjoint needs no scratch history
+                # per-level engine: the split adjoint streams the adjoint field of a chunk of shots through a scratch
+                # history -- the larger the chunk, the larger (and fewer) its launches: give it the HBM the forward history
+                # leaves free; the fused adjoint needs no scratch history
+                if "scratch_mb" not in user and "u_chunk_shots" not in user:
+                    per_shot = 4.0 * plan.nt * plan.level_floats()
+                    spare = 0.9 * (budget - plan.history_bytes(B, 0)) - 4.0 * plan.level_floats() * B * (2 * plan.ns + 4)
+                    if spare > 40e9:
+                        tiers.insert(0, (0, {"scratch_mb": int(spare / 1e6)}))
+                    elif spare >= per_shot:
+                        tiers.append((0, {"scratch_mb": int(spare / 1e6)}))
+                tiers.append((0, {"adj_mode": 1}))
             seg, extra = max(3, int(np.ceil(np.sqrt(2.0 * plan.nt)))), {}   # minimises pairs + segment levels
             for cand_seg, cand_extra in tiers:
                 if fits(cand_seg, **cand_extra):

@@ -49,10 +49,10 @@ def run_case(n, ns, B, nt, peak):
     pairs = B * ns * (n + 240) ** 2 * nt
     rate = pairs / ((f_ms + a_ms) * 1e-3)
     seg = plan.get("history_segment")
-    eng_f = "cluster C=%d" % plan.get("cluster_size_used") if plan.get("cluster_size_used") and not seg else "per-level"
+    eng_f = "cluster C=%d" % plan.get("cluster_size_used") if plan.get("cluster_size_used") and not seg and OPTS.get("engine") != 1 else "per-level"
     sp = plan.get("adj_split")
     eng_a = {1: "cluster split", 2: "cluster split, forward recomputed", 3: "per-level split"}.get(sp) or \
-        (("cluster fused C=%d" % plan.get("adj_cluster_size_used")) if plan.get("adj_cluster_size_used") and not seg else "per-level fused")
+        (("cluster fused C=%d" % plan.get("adj_cluster_size_used")) if plan.get("adj_cluster_size_used") and not seg and OPTS.get("engine") != 1 else "per-level fused")
     op.release_memory()
     return dict(n=n, ns=ns, B=B, nt=nt, forward_ms=f_ms, adjoint_ms=a_ms, pairs_per_s=rate, frac=rate * 28 / (peak * 1e9),
                 engine_fwd=eng_f, engine_adj=eng_a, history="checkpoint K=%d" % seg if seg else "full")
@@ -63,13 +63,14 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--min-n", type=int, default=0, help="only cases with interior n >= this")
+    ap.add_argument("--max-n", type=int, default=1 << 30, help="only cases with interior n <= this")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value")
     args = ap.parse_args()
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     rows = []
     global OPTS
     OPTS = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in args.opt)
-    for case in (CASES[:4] if args.quick else [c for c in CASES if c[0] >= args.min_n]):
+    for case in (CASES[:4] if args.quick else [c for c in CASES if args.min_n <= c[0] <= args.max_n]):
         try:
             rows.append(run_case(*case, peak))
         except Exception as ex:  # report and continue
