@@ -381,9 +381,9 @@ def main():
                                     % ((plan.history_bytes(B, seg) + plan.workspace_bytes(B)) / 1e9),
                        "history": ("none kept: forward field recomputed per chunk of %d shots in the backward pass" % plan.get("u_chunk_used")) if recompute
                                   else (("checkpoint pairs every %d levels" % seg) if seg else "every level"),
-                       "engine": {"forward": "cluster-resident (C=%d)" % plan.get("cluster_size_used") if fwd_cluster else "per-level",
+                       "engine": {"forward": "cluster-resident (C=%d, %d rows per thread)" % (plan.get("cluster_size_last"), plan.get("cluster_rows_last")) if fwd_cluster else "per-level",
                                   "adjoint": ("split: per-level tiled adjoint field + streaming imaging" if plan.get("adj_split") == 3 else
-                                              "split: cluster-resident adjoint field (C=%d) + streaming imaging" % plan.get("cluster_size_used")) if adj_split
+                                              "split: cluster-resident adjoint field (C=%d) + streaming imaging" % plan.get("cluster_size_last")) if adj_split
                                   else ("cluster-resident fused (C=%d)" % plan.get("adj_cluster_size_used") if adj_cluster else "per-level")},
                        "options": dict(op.options)},
             "e2e": {"value": e2e_value, "unit": "pairs/s",

@@ -72,11 +72,14 @@ int rdfwi_plan_destroy(rdfwi_plan plan);
  *   "u_chunk_shots"  shots per chunk of the split adjoint (0 = auto: whole waves of co-resident clusters)
  *   "scratch_mb"     cap on one scratch history of the split adjoint, MB (0 = 40000; 55000 for the recompute tier)
  *   "cluster_size" / "adj_cluster_size"  CTAs per cluster of the cluster-resident kernels (0 = smallest of 1..8 that fits)
+ *   "cluster_rows"   rows marched per thread by the cluster-resident time loop: 13, 7 or 4 (0 = auto: 13, or 7 / 4 on a
+ *                    wider cluster when a launch has so few shots that each still gets its own co-resident cluster)
  *   "rows_per_thread" (1, 2, 4, 8; tile rows = 8x) / "adj_rows_per_thread"  z-rows marched per thread, per-level kernels
  *   "chunk_models"   models advanced together by the per-level forward (0 = auto)
  *   "timing"         1 = record CUDA events around each kernel class on the caller's stream (read back as "us_<class>",
  *                    "n_<class>" with class in forward, adjoint_field, imaging, adjoint_loop)
- * rdfwi_plan_get additionally answers "pitch", "nzp", "nxp", "nt_out", "cluster_size_used", "adj_cluster_size_used",
+ * rdfwi_plan_get additionally answers "pitch", "nzp", "nxp", "nt_out", "cluster_size_used", "adj_cluster_size_used", "cluster_size_last", "cluster_rows_last" (what the
+ * last cluster-resident launch ran),
  * "cluster_wave" (co-resident clusters of the forward configuration), "adj_split" (what the last backward ran: 0 fused,
  * 1 cluster split, 2 cluster split on a recomputed forward history, 3 per-level split), "u_chunk_used". */
 int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value);

@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
 
 }  // namespace
 
-bool cluster_config(const Plan &p, ClusterConfig *cfg)
+// Smallest cluster (1..8 CTAs, or the non-portable 16) whose slabs fit when every thread marches R rows.
+static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, ClusterConfig *cfg)
 {
     const Grid &g = p.g;
     const int nthreads = p.cluster_threads == 256 ? 256 : kClusterThreads;
@@ -409,13 +410,13 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg)
         if (C > 8 && C != 16) continue;  // 1..8 are portable cluster sizes, 16 needs the non-portable opt-in
         // 16-CTA clusters (31-row slabs, 8 co-resident clusters) lose to the tiled per-level engine on the grids that
         // need them (interior 256^2: 1.25e11 vs 1.02e11 pairs/s at 16 shots, profiles/sweep_r1.md): only on request
-        if (C == 16 && p.cluster_size != 16 && p.engine != 2) continue;
+        if (C == 16 && !allow16 && p.cluster_size != 16 && p.engine != 2) continue;
         if (p.cluster_size > 0 && C != p.cluster_size) continue;
         if (g.nzp / C < 2) break;
         const int maxrows = (g.nzp + C - 1) / C;
-        const int ngroups = (maxrows + kClusterRowsMax - 1) / kClusterRowsMax;  // each thread marches kClusterRowsMax rows
+        const int ngroups = (maxrows + R - 1) / R;  // each thread marches R rows
         if (ngroups > groups_max) continue;
-        const int slabrows = ngroups * kClusterRowsMax;  // >= maxrows: rows past the slab are computed but never stored
+        const int slabrows = ngroups * R;  // >= maxrows: rows past the slab are computed but never stored
         size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + g.nxp + 1 + g.nrec + 2 * g.nxp + 2 * g.nrec) * sizeof(float);
         if (smem > (size_t)max_smem) continue;
         const size_t room = nthreads == 256 ? (size_t)(113 * 1024) : (size_t)max_smem;  // two CTAs per SM must fit 228 KB
@@ -424,15 +425,35 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg)
         if (cfg->wav_smem) smem += (size_t)p.nt * sizeof(float);
         cfg->nthreads = nthreads;
         cfg->C = C; cfg->maxrows = maxrows; cfg->ngroups = ngroups; cfg->slabrows = slabrows; cfg->smem = smem;
+        cfg->rmax = R;
         return true;
     }
     return false;
 }
 
-template <int PITCH, bool ADJ, int NT>
+bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots)
+{
+    if (p.cluster_rows > 0) return cluster_config_rows(p, p.cluster_rows, true, cfg);  // forced (tests, tuning)
+    if (!cluster_config_rows(p, kClusterRowsMax, false, cfg)) return false;
+    if (nshots <= 0 || p.cluster_size != 0 || p.cluster_threads == 256) return true;
+    // Few shots (one model of the reference's configs has 5): the throughput configuration would occupy nshots * C of
+    // the 148 SMs and every level would still cost a full 13-row sweep.  A level is latency-bound (one shot's level takes
+    // the same time alone as among 33 co-resident ones), so spread a shot over more CTAs with fewer rows per thread --
+    // as long as every shot of the launch still gets its own co-resident cluster.
+    if (2 * nshots * cfg->C > 148) return true;
+    static const int kWideRows[2] = {4, 7};
+    for (int i = 0; i < 2; ++i) {
+        ClusterConfig wide;
+        if (!cluster_config_rows(p, kWideRows[i], true, &wide) || wide.C <= cfg->C) continue;
+        if (fwd_cluster_wave(p, wide) >= nshots) { *cfg = wide; return true; }
+    }
+    return true;
+}
+
+template <int R, int PITCH, bool ADJ, int NT>
 static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st, int *wave_only)
 {
-    auto kernel = k_fwd_cluster<kClusterRowsMax, PITCH, ADJ, NT>;
+    auto kernel = k_fwd_cluster<R, PITCH, ADJ, NT>;
     a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
 
     cudaLaunchConfig_t cfg{};
@@ -484,22 +505,37 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
     return e;
 }
 
+template <int R>
+static cudaError_t dispatch_fwd_cluster_r(const Plan &p, const ClusterConfig &cc, const ClusterFwdArgs &a, cudaStream_t st, int *wave_only)
+{
+    const bool adj = a.adj_mode != 0;
+    switch (p.g.pitch) {  // production grids get immediate row offsets (OpenFWI 310+2, Marmousi/Overthrust 430+2)
+        case 312: return adj ? launch_fwd_cluster_t<R, 312, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 312, false, 512>(p, cc, a, st, wave_only);
+        case 432: return adj ? launch_fwd_cluster_t<R, 432, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 432, false, 512>(p, cc, a, st, wave_only);
+        default: return adj ? launch_fwd_cluster_t<R, 0, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 0, false, 512>(p, cc, a, st, wave_only);
+    }
+}
+
 static cudaError_t dispatch_fwd_cluster(const Plan &p, const ClusterConfig &cc, const ClusterFwdArgs &a, cudaStream_t st, int *wave_only)
 {
     const bool adj = a.adj_mode != 0;
-    if (cc.nthreads == 256) {  // two CTAs per SM (experimental; OpenFWI pitch and runtime pitch only)
-        if (p.g.pitch == 312) return adj ? launch_fwd_cluster_t<312, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<312, false, 256>(p, cc, a, st, wave_only);
-        return adj ? launch_fwd_cluster_t<0, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<0, false, 256>(p, cc, a, st, wave_only);
+    if (cc.nthreads == 256) {  // two CTAs per SM (experimental; OpenFWI pitch and runtime pitch only, 13 rows per thread)
+        if (cc.rmax != kClusterRowsMax) return cudaErrorInvalidValue;
+        if (p.g.pitch == 312) return adj ? launch_fwd_cluster_t<kClusterRowsMax, 312, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<kClusterRowsMax, 312, false, 256>(p, cc, a, st, wave_only);
+        return adj ? launch_fwd_cluster_t<kClusterRowsMax, 0, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<kClusterRowsMax, 0, false, 256>(p, cc, a, st, wave_only);
     }
-    switch (p.g.pitch) {  // production grids get immediate row offsets (OpenFWI 310+2, Marmousi/Overthrust 430+2)
-        case 312: return adj ? launch_fwd_cluster_t<312, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<312, false, 512>(p, cc, a, st, wave_only);
-        case 432: return adj ? launch_fwd_cluster_t<432, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<432, false, 512>(p, cc, a, st, wave_only);
-        default: return adj ? launch_fwd_cluster_t<0, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<0, false, 512>(p, cc, a, st, wave_only);
+    switch (cc.rmax) {  // rows marched per thread: 13 for throughput, 7 / 4 on wider clusters when the shots are few
+        case kClusterRowsMax: return dispatch_fwd_cluster_r<kClusterRowsMax>(p, cc, a, st, wave_only);
+        case 7: return dispatch_fwd_cluster_r<7>(p, cc, a, st, wave_only);
+        case 4: return dispatch_fwd_cluster_r<4>(p, cc, a, st, wave_only);
+        default: return cudaErrorInvalidValue;
     }
 }
 
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
 {
+    const_cast<Plan &>(p).last_fwd_C = cc.C;
+    const_cast<Plan &>(p).last_fwd_rows = cc.rmax;
     return dispatch_fwd_cluster(p, cc, a, st, nullptr);
 }
 
@@ -508,6 +544,9 @@ cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFw
 // SMs / C when the occupancy query is not available (no device).
 int fwd_cluster_wave(const Plan &p, const ClusterConfig &cc)
 {
+    const int key = (cc.C * 64 + cc.rmax) * 1024 + cc.nthreads;
+    for (int i = 0; i < p.wave_n; ++i)
+        if (p.wave_keys[i] == key) return p.wave_vals[i];
     ClusterFwdArgs a{};
     a.adj_mode = 1;
     int wave = 0;
@@ -517,6 +556,8 @@ int fwd_cluster_wave(const Plan &p, const ClusterConfig &cc)
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
         wave = sms / cc.C > 0 ? sms / cc.C : 1;
     }
+    const int slot = p.wave_n < 8 ? p.wave_n++ : 7;
+    p.wave_keys[slot] = key; p.wave_vals[slot] = wave;
     return wave;
 }
 

@@ -119,12 +119,7 @@ struct Workspace {
     float *p_hist = nullptr;  // recompute mode: forward history of one chunk of shots
 };
 
-int cached_wave(const Plan &p, const ClusterConfig &cc)
-{
-    const int key = cc.C * 1024 + cc.nthreads;
-    if (p.wave_key != key) { p.wave_val = fwd_cluster_wave(p, cc); p.wave_key = key; }
-    return p.wave_val;
-}
+int cached_wave(const Plan &p, const ClusterConfig &cc) { return fwd_cluster_wave(p, cc); }  // cached per configuration
 
 Workspace carve(const Plan &p, int B, void *base)
 {
@@ -357,6 +352,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "img_prefetch") { if (value < 0 || value > 64) goto bad; p->img_prefetch = (int)value; }
     else if (k == "trace_ptr") { p->trace_ptr = reinterpret_cast<long long *>(value); }
     else if (k == "cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->cluster_size = (int)value; }
+    else if (k == "cluster_rows") { if (value != 0 && value != 4 && value != 7 && value != kClusterRowsMax) goto bad; p->cluster_rows = (int)value; }
     else if (k == "adj_cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->adj_cluster_size = (int)value; }
     else { set_error("unknown option " + k); return RDFWI_EINVAL; }
     return RDFWI_OK;
@@ -391,6 +387,9 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
     else if (k == "scratch_mb") *out = p->scratch_mb;
     else if (k == "cluster_wave") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cached_wave(*p, cc) : 0; }
     else if (k == "cluster_size") *out = p->cluster_size;
+    else if (k == "cluster_rows") *out = p->cluster_rows;
+    else if (k == "cluster_size_last") *out = p->last_fwd_C;
+    else if (k == "cluster_rows_last") *out = p->last_fwd_rows;
     else if (k == "cluster_size_used") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cc.C : 0; }
     else if (k == "adj_cluster_size_used") { ClusterConfig cc; *out = adj_cluster_config(*p, &cc) ? cc.C : 0; }
     else if (k == "pitch") *out = p->g.pitch;
@@ -451,7 +450,7 @@ int rdfwi_forward(rdfwi_plan plan, const float *v, int32_t B, float *seis, void 
     if (hist && w.recompute) hist = nullptr;  // nothing is kept: the backward pass recomputes the forward field
     const bool ckpt = hist && segment > 0;  // checkpointed history: per-level engine
     ClusterConfig cc;
-    if (p.engine != 1 && !ckpt && cluster_config(p, &cc)) {
+    if (p.engine != 1 && !ckpt && cluster_config(p, &cc, B * g.ns)) {
         // cluster-resident time loop: one launch for all shots and all levels
         ClusterFwdArgs a{};
         a.alpha = w.alpha; a.kap = w.kap; a.beta_src = w.beta_src;
@@ -537,7 +536,7 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     ClusterConfig cc;
     const_cast<Plan &>(p).last_split = (!ckpt && w.split) ? (w.recompute ? 2 : 1) : 0;
     const_cast<Plan &>(p).last_u_chunk = w.u_chunk;
-    if (!ckpt && w.split && cluster_config(p, &cc)) {
+    if (!ckpt && w.split && cluster_config(p, &cc, std::min(w.u_chunk, B * g.ns))) {
         // split adjoint: per chunk of shots, (1) the cluster-resident kernel runs the adjoint field in the u-variable
         // and streams it to HBM, (2) a streaming kernel forms the imaging sums from the two histories
         const int nshots = B * g.ns;

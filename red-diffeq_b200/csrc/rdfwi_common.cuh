@@ -60,6 +60,7 @@ struct Plan {
     int adj_rows_per_thread = 1;
     int engine = 0;         // 0 = auto, 1 = per-level kernels, 2 = cluster-resident time loop
     int cluster_size = 0;   // 0 = smallest cluster that fits
+    int cluster_rows = 0;   // rows marched per thread of k_fwd_cluster: 0 = auto (13; 7 or 4 on wider clusters for few shots)
     int adj_cluster_size = 0;
     int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused k_adj_cluster
     int cluster_threads = 0;  // 0/512 = one 512-thread CTA per SM; 256 = two 256-thread CTAs per SM (k_fwd_cluster)
@@ -75,7 +76,8 @@ struct Plan {
     int history_segment = 0;  // 0 = keep every level; K >= 3 = checkpoint pairs every K levels, recompute in the backward pass
                               // (K >= nt: no history at all -- the backward pass recomputes the forward field chunk by chunk)
     long long scratch_mb = 0; // cap on ONE scratch history of the split adjoint, MB (0 = 40000)
-    mutable int wave_key = -1, wave_val = 0;  // cached fwd_cluster_wave() of the configuration in use
+    mutable int wave_keys[8] = {0}, wave_vals[8] = {0}, wave_n = 0;  // cached fwd_cluster_wave() per configuration
+    int last_fwd_C = 0, last_fwd_rows = 0;  // configuration of the last k_fwd_cluster launch (reported by rdfwi_plan_get)
 };
 
 // Cluster-resident forward time loop (kernels_cluster.cu).
@@ -118,10 +120,10 @@ struct ClusterAdjArgs {
 struct ClusterConfig {
     int C = 0;        // CTAs per cluster = row slabs per shot
     int maxrows = 0;  // rows of the largest slab
-    int ngroups = 0;  // row groups per CTA (threads = ngroups * q4), kClusterRowsMax rows per thread
-    int slabrows = 0; // ngroups * kClusterRowsMax >= maxrows (rows allocated per buffer, halos excluded)
+    int ngroups = 0;  // row groups per CTA (threads = ngroups * q4), rmax rows per thread
+    int slabrows = 0; // ngroups * rmax >= maxrows (rows allocated per buffer, halos excluded)
     size_t smem = 0;  // dynamic shared memory per CTA
-    int rmax = 0;     // rows per thread (template instantiation) of the adjoint kernel
+    int rmax = 0;     // rows per thread (template instantiation)
     bool wav_smem = false;  // the wavelet is staged in shared memory
     int nthreads = 512;     // threads per CTA
 };
@@ -179,7 +181,10 @@ cudaError_t launch_step_tile(const Plan &p, const StepArgs &a, cudaStream_t st);
 cudaError_t launch_adj_step(const Plan &p, const AdjArgs &a, int nb, cudaStream_t st);
 int adj_shot_slices(const Plan &p, int nb);  // imaging planes per model the per-level adjoint accumulates into
 // kernels_cluster.cu
-bool cluster_config(const Plan &p, ClusterConfig *cfg);
+// nshots = 0: the throughput configuration (smallest cluster that fits, 13 rows per thread).  nshots > 0: the
+// configuration for a launch of that many shots -- when they are so few that they leave most SMs idle, a wider cluster
+// with fewer rows per thread (shorter sweeps, same arithmetic per cell) as long as all shots stay co-resident.
+bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots = 0);
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st);
 int fwd_cluster_wave(const Plan &p, const ClusterConfig &cc);  // co-resident clusters = shots in flight per wave
 // kernels_cluster_adj.cu

@@ -131,6 +131,49 @@ def test_recomputed_history_matches_full_history(name, chunk):
     assert rel_l2(g1, g.grad_f32) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("name,rows,csize", [("tiny_default", 4, 0), ("tiny_default", 4, 3), ("tiny_custom", 7, 2),
+                                             ("tiny_half_receivers", 4, 5), ("tiny_half_receivers", 7, 0),
+                                             ("openfwi", 7, 0), ("openfwi", 4, 0), ("marmousi", 7, 0), ("marmousi", 13, 8)])
+def test_wide_cluster_configurations(name, rows, csize):
+    """Few-shot configurations of the cluster-resident time loop (a shot spread over more CTAs, 7 or 4 rows marched per
+    thread instead of 13): same arithmetic per cell => seismograms bit-identical to the reference fixtures and gradients
+    bit-identical to the throughput configuration (13 rows, smallest cluster)."""
+    g = Golden(name)
+    base = _op(g)
+    base.set_option("engine", 2)
+    base.set_option("cluster_rows", 13)
+    wide = _op(g)
+    wide.set_option("engine", 2)
+    wide.set_option("cluster_rows", rows)
+    if csize:
+        wide.set_option("cluster_size", csize)
+    shape = (g.v.shape[0], len(base.ctx["sx"]), -(-g.ctx["nt"] // g.sample_temporal), len(base.ctx["gx"]))
+    cot = g.cotangent(shape)
+    s0, g0 = _run(base, g.v, cot)
+    s1, g1 = _run(wide, g.v, cot)
+    plan = wide._plan_for(g.v.shape[2], g.v.shape[3], torch.device("cuda:0"))
+    assert plan.get("cluster_rows_last") == rows and (csize == 0 or plan.get("cluster_size_last") == csize)
+    assert np.array_equal(s1[:, :, ::g.seis_stride, :], g.seis_f32)
+    assert np.array_equal(s0, s1)
+    assert np.array_equal(g0, g1)
+    assert rel_l2(g1, g.grad_f32) <= GRAD_TOL
+
+
+def test_few_shots_pick_a_wide_cluster():
+    """One OpenFWI model (5 shots) would occupy 20 SMs with the throughput configuration: the automatic choice is a wider
+    cluster with fewer rows per thread; a batch that fills the GPU keeps 13 rows per thread."""
+    g = Golden("openfwi")
+    op = _op(g)
+    s, _ = _run(op, g.v)
+    plan = op._plan_for(70, 70, torch.device("cuda:0"))
+    assert np.array_equal(s[:, :, ::g.seis_stride, :], g.seis_f32)
+    assert plan.get("cluster_rows_last") in (4, 7) and plan.get("cluster_size_last") > plan.get("cluster_size_used")
+    many = np.repeat(g.v, 16, axis=0)
+    s16, _ = _run(op, many)
+    assert plan.get("cluster_rows_last") == 13 and plan.get("cluster_size_last") == plan.get("cluster_size_used")
+    assert np.array_equal(s16[3:4], s)
+
+
 @pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "per-level-checkpointed", "cluster-split", "cluster-fused"])
 def test_many_shots_per_model(engine, oracle):
     """More shots than any golden case (ns = 11: the per-level adjoint deals them over several grid.z slices, each with its
