@@ -132,7 +132,21 @@ int rdfwi_coefficients(rdfwi_plan plan, const float *v_phys, int32_t B, float *a
                        float *kappa_tab, float *velmin, int32_t *argmin, float *beta_src,
                        void *workspace, size_t workspace_bytes, void *stream);
 
-/* Number of kernel launches enqueued by this thread's last rdfwi_forward / rdfwi_backward call. */
+/*
+ * Data misfit of the inversion loop in one pass (opt-in, beyond the drop-in operator): what
+ * LossCalculator.observation_loss (core/losses.py:27-40) and its autograd compute with ~10 elementwise ATen kernels.
+ *   seis, observed : device, (B, ns, nt_out, nrec) fp32 (the plan's seismogram shape), modelled / observed data
+ *   mask           : device, same shape, 1 = observed trace sample, 0 = missing (core/inversion.py:66); NULL = all ones
+ *   stats          : device, (B, 2) float64, written: [b][0] = sum |observed - seis| * mask, [b][1] = sum mask.
+ *                    The reference's loss is stats[b][0] / max(stats[b][1], 1)  (losses.py:36; the mean when mask is NULL)
+ *   sign_out       : device, same shape as seis (may alias seis) or NULL: mask * sign(seis - observed), i.e.
+ *                    d stats[b][0] / d seis -- scaled by g_b / count_b it is the cotangent rdfwi_backward takes
+ *   workspace      : >= 512 * B bytes of scratch (the forward workspace may be reused)
+ */
+int rdfwi_misfit_l1(rdfwi_plan plan, const float *seis, const float *observed, const float *mask, int32_t B,
+                    double *stats, float *sign_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Number of kernel launches enqueued by this thread's last rdfwi_forward / rdfwi_backward / rdfwi_misfit_l1 call. */
 int64_t rdfwi_last_launch_count(void);
 
 #ifdef __cplusplus

@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "librdfwi.so")
-SOURCES = ["rdfwi_api.cu", "kernels_prologue.cu", "kernels_step.cu", "kernels_tile.cu", "kernels_cluster.cu", "kernels_cluster_adj.cu", "kernels_imaging.cu", "kernels_epilogue.cu"]
+SOURCES = ["rdfwi_api.cu", "kernels_prologue.cu", "kernels_step.cu", "kernels_tile.cu", "kernels_cluster.cu", "kernels_cluster_adj.cu", "kernels_imaging.cu", "kernels_epilogue.cu", "kernels_misfit.cu"]
 HEADERS = [os.path.join(_CSRC, "rdfwi_common.cuh"), os.path.join(_CSRC, "cluster_ptx.cuh"), os.path.join(_ROOT, "include", "rdfwi.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # every symbol include/rdfwi.h declares
 EXPORTS = ["rdfwi_version", "rdfwi_last_error", "rdfwi_plan_create", "rdfwi_plan_destroy", "rdfwi_plan_set",
            "rdfwi_plan_get", "rdfwi_level_floats", "rdfwi_workspace_bytes", "rdfwi_history_bytes", "rdfwi_forward",
-           "rdfwi_backward", "rdfwi_coefficients", "rdfwi_last_launch_count"]
+           "rdfwi_backward", "rdfwi_coefficients", "rdfwi_misfit_l1", "rdfwi_last_launch_count"]
 
 
 class RdfwiError(RuntimeError):
@@ -84,9 +84,10 @@ def load():
     lib.rdfwi_forward.argtypes = [vp, vp, i32, vp, vp, sz, vp, sz, i32, vp]
     lib.rdfwi_backward.argtypes = [vp, vp, i32, vp, vp, vp, sz, vp, sz, i32, vp]
     lib.rdfwi_coefficients.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.rdfwi_misfit_l1.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, sz, vp]
     lib.rdfwi_last_launch_count.restype = i64
     for name in ("rdfwi_plan_create", "rdfwi_plan_destroy", "rdfwi_plan_set", "rdfwi_plan_get", "rdfwi_forward",
-                 "rdfwi_backward", "rdfwi_coefficients"):
+                 "rdfwi_backward", "rdfwi_coefficients", "rdfwi_misfit_l1"):
         getattr(lib, name).restype = ctypes.c_int
     _lib = lib
     return lib
@@ -156,6 +157,10 @@ class Plan:
     def coefficients(self, v_ptr, B, alpha_ptr, kap_ptr, velmin_ptr, argmin_ptr, beta_ptr, ws_ptr, ws_bytes, stream):
         _check(load().rdfwi_coefficients(self._h, v_ptr, B, alpha_ptr, kap_ptr, velmin_ptr, argmin_ptr, beta_ptr, ws_ptr,
                                          ws_bytes, stream), "rdfwi_coefficients")
+
+    def misfit_l1(self, seis_ptr, obs_ptr, mask_ptr, B, stats_ptr, sign_ptr, ws_ptr, ws_bytes, stream):
+        _check(load().rdfwi_misfit_l1(self._h, seis_ptr, obs_ptr, mask_ptr, B, stats_ptr, sign_ptr, ws_ptr, ws_bytes, stream),
+               "rdfwi_misfit_l1")
 
     @staticmethod
     def last_launch_count():

@@ -405,7 +405,7 @@ static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, 
     const int groups_max = nthreads / g.q4;
     if (groups_max < 1) return false;
     int max_smem = 0;
-    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device) != cudaSuccess) return false;
+    if (device_attr(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device) != cudaSuccess) return false;
     for (int C = 1; C <= 16; ++C) {
         if (C > 8 && C != 16) continue;  // 1..8 are portable cluster sizes, 16 needs the non-portable opt-in
         // 16-CTA clusters (31-row slabs, 8 co-resident clusters) lose to the tiled per-level engine on the grids that
@@ -488,7 +488,7 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
             }
         }
         int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+        device_attr(&sms, cudaDevAttrMultiProcessorCount, p.device);
         cfg.gridDim = dim3((unsigned)(sms / cc.C * cc.C));
         int q = 0;
         e = cudaOccupancyMaxActiveClusters(&q, kernel, &cfg);
@@ -553,7 +553,7 @@ int fwd_cluster_wave(const Plan &p, const ClusterConfig &cc)
     if (dispatch_fwd_cluster(p, cc, a, nullptr, &wave) != cudaSuccess || wave < 1) {
         cudaGetLastError();
         int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+        device_attr(&sms, cudaDevAttrMultiProcessorCount, p.device);
         wave = sms / cc.C > 0 ? sms / cc.C : 1;
     }
     const int slot = p.wave_n < 8 ? p.wave_n++ : 7;

@@ -412,7 +412,7 @@ cudaError_t launch_adj_cluster_t(const Plan &p, const ClusterConfig &cc, Cluster
     cfg.dynamicSmemBytes = cc.smem;
     cfg.stream = st;
     int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+    device_attr(&sms, cudaDevAttrMultiProcessorCount, p.device);
     cfg.gridDim = dim3((unsigned)(sms / cc.C * cc.C));
     int max_clusters = 0;
     e = cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg);
@@ -431,7 +431,7 @@ cudaError_t launch_adj_cluster_t(const Plan &p, const ClusterConfig &cc, Cluster
 bool adj_cluster_config(const Plan &p, ClusterConfig *cfg)
 {
     int max_smem = 0;
-    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device) != cudaSuccess) return false;
+    if (device_attr(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device) != cudaSuccess) return false;
     ClusterConfig best;
     bool found = false;
     ClusterConfig c;

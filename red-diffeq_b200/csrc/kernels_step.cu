@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) k_adj_step(AdjArgs a, Grid g)
 int shot_slices(const Plan &p, int blocks_xy, int nb, int min_per_slice)
 {
     int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+    device_attr(&sms, cudaDevAttrMultiProcessorCount, p.device);
     const int want = (2 * 2 * sms + blocks_xy * nb - 1) / (blocks_xy * nb);  // 2 waves at ~2 CTAs per SM
     int sz = std::min(want, std::max(1, p.g.ns / min_per_slice));
     return std::max(1, std::min(sz, p.g.ns));

@@ -87,7 +87,7 @@ int chunk_models(const Plan &p, int B)
     int nb = p.chunk_models;
     if (nb <= 0) {
         int l2 = 0;
-        if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p.device) != cudaSuccess || l2 <= 0) l2 = 64 << 20;
+        if (device_attr(&l2, cudaDevAttrL2CacheSize, p.device) != cudaSuccess || l2 <= 0) l2 = 64 << 20;
         // three live levels (p_{t-1}, p_{t-2}, p_t) of every shot of the chunk in ~40% of L2
         const double per_model = 3.0 * p.g.ns * (double)p.g.level * sizeof(float);
         nb = (int)std::max(1.0, std::floor(0.4 * l2 / per_model));
@@ -679,6 +679,26 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     delete timed_adj;
     // the per-level engine accumulated into pl_slices planes per model (one per grid.z slice of shots)
     RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, pl_slices, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
+    return RDFWI_OK;
+}
+
+int rdfwi_misfit_l1(rdfwi_plan plan, const float *seis, const float *observed, const float *mask, int32_t B,
+                    double *stats, float *sign_out, void *ws, size_t ws_bytes, void *stream)
+{
+    if (!plan) { set_error("null plan"); return RDFWI_EINVAL; }
+    if (!seis || !observed || !stats || B <= 0) { set_error("null seismogram / observed / stats pointer or B <= 0"); return RDFWI_EINVAL; }
+    if (!ws || ws_bytes < misfit_scratch_bytes(B)) { set_error("workspace too small for the misfit partial sums"); return RDFWI_ESIZE; }
+    if ((reinterpret_cast<uintptr_t>(ws) & 7) != 0) { set_error("workspace must be 8-byte aligned"); return RDFWI_EINVAL; }
+    const Plan &p = *reinterpret_cast<Plan *>(plan);
+    const long long n = (long long)p.g.ns * p.g.nt_out * p.g.nrec;
+    if ((n & 3) == 0 && (((reinterpret_cast<uintptr_t>(seis) | reinterpret_cast<uintptr_t>(observed) | reinterpret_cast<uintptr_t>(mask) |
+                           reinterpret_cast<uintptr_t>(sign_out)) & 15) != 0)) {
+        set_error("seismogram buffers must be 16-byte aligned");
+        return RDFWI_EINVAL;
+    }
+    DeviceGuard guard(p.device);
+    t_launches = 0;
+    RD_CUDA(launch_misfit_l1(seis, observed, mask, B, n, sign_out, stats, static_cast<double *>(ws), (cudaStream_t)stream));
     return RDFWI_OK;
 }
 

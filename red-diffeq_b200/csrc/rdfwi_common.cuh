@@ -169,6 +169,20 @@ struct AdjArgs {
     int slices;                 // grid.z slices the shots are dealt over = imaging planes per model (Ga, Gk)
 };
 
+// cudaDeviceGetAttribute, asked once per (device, attribute): the answers never change, and the library is called inside
+// CUDA-graph capture (core/inversion.py), where the fewer runtime queries the better.
+inline cudaError_t device_attr(int *value, cudaDeviceAttr attr, int device)
+{
+    static int cache[64][3];
+    static bool have[64][3] = {};
+    const int slot = attr == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 0 : attr == cudaDevAttrMultiProcessorCount ? 1 : 2;
+    const int d = device & 63;
+    if (have[d][slot]) { *value = cache[d][slot]; return cudaSuccess; }
+    const cudaError_t e = cudaDeviceGetAttribute(value, attr, device);
+    if (e == cudaSuccess) { cache[d][slot] = *value; have[d][slot] = true; }
+    return e;
+}
+
 void set_error(const std::string &msg);
 void count_launch();
 
@@ -198,5 +212,10 @@ cudaError_t launch_imaging(const Plan &p, const float *phist, const float *uhist
 cudaError_t launch_gradient_epilogue(const Plan &p, const float *v, int B, const float *Ga, const float *Gk,
                                      const float *Gb, int planes, const int *argmin, float *fold_tmp,
                                      double *vel_part, float *grad_v, cudaStream_t st);
+
+// kernels_misfit.cu: per-model masked L1 sums + sign field of the seismogram residual (core/losses.py:27-40)
+size_t misfit_scratch_bytes(int B);
+cudaError_t launch_misfit_l1(const float *seis, const float *obs, const float *mask, int B, long long n, float *sign_out,
+                             double *stats, double *part, cudaStream_t st);
 
 }  // namespace rdfwi

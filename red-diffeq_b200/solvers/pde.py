@@ -44,62 +44,111 @@ class _HistoryLease:
             pass
 
 
+def _solve_forward(ctx, v_phys, op, need_grad):
+    """Runs rdfwi_forward for a (B, 1, nz, nx) velocity batch in m/s; keeps what the adjoint pass needs on ctx."""
+    if v_phys.dim() != 4 or v_phys.shape[1] != 1:
+        raise ValueError(f"expected a (B, 1, nz, nx) velocity batch, got {tuple(v_phys.shape)}")
+    if not v_phys.is_cuda:
+        raise RuntimeError("rdfwi: the velocity batch must live on a CUDA device (there is no CPU fallback)")
+    if v_phys.dtype != torch.float32:
+        raise TypeError(f"rdfwi computes in fp32 like the reference; got {v_phys.dtype}")
+    v = v_phys.detach().contiguous()
+    B, _, nz, nx = v.shape
+    plan = op._plan_for(nz, nx, v.device)
+    with torch.cuda.device(v.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        hist, hist_bytes, lease, segment = None, 0, None, 0
+        if need_grad:
+            segment = op._choose_segment(plan, B, v.device)
+            hist_bytes = plan.history_bytes(B, segment)
+            lease = op._lease_history(hist_bytes, v.device)
+            hist = lease.buffer
+        seis = torch.empty((B, plan.ns, plan.nt_out, plan.nrec), dtype=torch.float32, device=v.device)
+        ws_bytes = plan.workspace_bytes(B)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
+        plan.forward(v.data_ptr(), B, seis.data_ptr(), ws.data_ptr(), ws_bytes,
+                     hist.data_ptr() if hist is not None else None, hist_bytes, segment, stream)
+        op.last_launches = plan.last_launch_count()
+    if need_grad:
+        ctx.op, ctx.plan, ctx.hist, ctx.hist_bytes, ctx.segment = op, plan, lease, hist_bytes, segment
+        ctx.v = v
+    return seis, plan, ws, ws_bytes
+
+
+def _solve_backward(ctx, grad_seis):
+    """Runs rdfwi_backward with the cotangent of the seismograms; returns d loss / d v_phys."""
+    v = ctx.v
+    plan, lease = ctx.plan, ctx.hist
+    if lease is None:
+        raise RuntimeError("rdfwi: backward called twice or without saved history")
+    hist = lease.buffer
+    B = v.shape[0]
+    g = grad_seis.contiguous()
+    if g.dtype != torch.float32:
+        g = g.float()
+    with torch.cuda.device(v.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        grad_v = torch.empty_like(v)
+        ws_bytes = plan.workspace_bytes(B)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
+        plan.backward(v.data_ptr(), B, g.data_ptr(), grad_v.data_ptr(), ws.data_ptr(), ws_bytes,
+                      hist.data_ptr() if hist is not None else None, ctx.hist_bytes, ctx.segment, stream)
+        ctx.op.last_launches += plan.last_launch_count()
+    ctx.hist = None  # first-order only, like every caller in the reference
+    ctx.v = None
+    lease.release()  # hand the wavefield history back to the operator's arena
+    return grad_v
+
+
 class _WaveSolve(torch.autograd.Function):
     """seismograms = F(v_phys); backward = discrete adjoint."""
 
     @staticmethod
     def forward(ctx, v_phys, op):
-        if v_phys.dim() != 4 or v_phys.shape[1] != 1:
-            raise ValueError(f"expected a (B, 1, nz, nx) velocity batch, got {tuple(v_phys.shape)}")
-        if not v_phys.is_cuda:
-            raise RuntimeError("rdfwi: the velocity batch must live on a CUDA device (there is no CPU fallback)")
-        if v_phys.dtype != torch.float32:
-            raise TypeError(f"rdfwi computes in fp32 like the reference; got {v_phys.dtype}")
-        v = v_phys.detach().contiguous()
-        B, _, nz, nx = v.shape
-        plan = op._plan_for(nz, nx, v.device)
-        need_grad = ctx.needs_input_grad[0]
-        with torch.cuda.device(v.device):
-            stream = torch.cuda.current_stream().cuda_stream
-            hist, hist_bytes, lease, segment = None, 0, None, 0
-            if need_grad:
-                segment = op._choose_segment(plan, B, v.device)
-                hist_bytes = plan.history_bytes(B, segment)
-                lease = op._lease_history(hist_bytes, v.device)
-                hist = lease.buffer
-            seis = torch.empty((B, plan.ns, plan.nt_out, plan.nrec), dtype=torch.float32, device=v.device)
-            ws_bytes = plan.workspace_bytes(B)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
-            plan.forward(v.data_ptr(), B, seis.data_ptr(), ws.data_ptr(), ws_bytes,
-                         hist.data_ptr() if hist is not None else None, hist_bytes, segment, stream)
-            op.last_launches = plan.last_launch_count()
-        if need_grad:
-            ctx.op, ctx.plan, ctx.hist, ctx.hist_bytes, ctx.segment = op, plan, lease, hist_bytes, segment
-            ctx.save_for_backward(v)
+        seis, _plan, _ws, _n = _solve_forward(ctx, v_phys, op, ctx.needs_input_grad[0])
         return seis
 
     @staticmethod
     def backward(ctx, grad_seis):
-        (v,) = ctx.saved_tensors
-        plan, lease = ctx.plan, ctx.hist
-        if lease is None:
-            raise RuntimeError("rdfwi: backward called twice or without saved history")
-        hist = lease.buffer
-        B = v.shape[0]
-        g = grad_seis.contiguous()
-        if g.dtype != torch.float32:
-            g = g.float()
-        with torch.cuda.device(v.device):
+        return _solve_backward(ctx, grad_seis), None
+
+
+class _WaveMisfit(torch.autograd.Function):
+    """stats = (sum |y - F(v)| * mask, sum mask) per model, the seismograms never leaving the library as a torch graph.
+
+    Forward: rdfwi_forward, then rdfwi_misfit_l1 turns the seismogram buffer IN PLACE into the sign field
+    mask * sign(F(v) - y).  Backward: cotangent = sign field * d loss / d stats[:, 0] (one broadcast multiply),
+    rdfwi_backward.  Replaces the ~10 elementwise kernels of core/losses.py:27-40 and their autograd."""
+
+    @staticmethod
+    def forward(ctx, v_phys, y, mask, op, keep_seis):
+        need_grad = ctx.needs_input_grad[0]
+        seis, plan, ws, ws_bytes = _solve_forward(ctx, v_phys, op, need_grad)
+        B = seis.shape[0]
+        if tuple(y.shape) != tuple(seis.shape):
+            raise ValueError(f"observed data {tuple(y.shape)} does not match the modelled seismograms {tuple(seis.shape)}")
+        if mask is not None and tuple(mask.shape) != tuple(seis.shape):
+            raise ValueError(f"mask {tuple(mask.shape)} does not match the modelled seismograms {tuple(seis.shape)}")
+        y = y.to(device=seis.device, dtype=torch.float32).contiguous()
+        m = None if mask is None else mask.to(device=seis.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(seis.device):
             stream = torch.cuda.current_stream().cuda_stream
-            grad_v = torch.empty_like(v)
-            ws_bytes = plan.workspace_bytes(B)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
-            plan.backward(v.data_ptr(), B, g.data_ptr(), grad_v.data_ptr(), ws.data_ptr(), ws_bytes,
-                          hist.data_ptr(), ctx.hist_bytes, ctx.segment, stream)
-            ctx.op.last_launches += plan.last_launch_count()
-        ctx.hist = None  # first-order only, like every caller in the reference
-        lease.release()  # hand the wavefield history back to the operator's arena
-        return grad_v, None
+            stats = torch.empty((B, 2), dtype=torch.float64, device=seis.device)
+            sign = torch.empty_like(seis) if keep_seis else seis
+            plan.misfit_l1(seis.data_ptr(), y.data_ptr(), m.data_ptr() if m is not None else None, B, stats.data_ptr(),
+                           sign.data_ptr() if need_grad else None, ws.data_ptr(), ws_bytes, stream)
+            op.last_launches += plan.last_launch_count()
+        if need_grad:
+            ctx.sign = sign
+        ctx.mark_non_differentiable(*([seis] if keep_seis else []))
+        return (stats, seis) if keep_seis else (stats,)
+
+    @staticmethod
+    def backward(ctx, grad_stats, *_unused):
+        g = grad_stats[:, 0].to(torch.float32).view(-1, 1, 1, 1)
+        cot = ctx.sign.mul_(g)  # in place: the sign field is this Function's own buffer
+        ctx.sign = None
+        return _solve_backward(ctx, cot), None, None, None, None
 
 
 class FWIForward(nn.Module):
@@ -263,6 +312,27 @@ class FWIForward(nn.Module):
             v = self.v_denorm_func(v)
         s = _WaveSolve.apply(v, self)
         return self.s_norm_func(s) if self.normalize else s
+
+    def misfit_stats(self, v, y, mask=None, return_seismograms=False):
+        """Per-model L1 data-misfit sums without materialising the residual as torch tensors (opt-in extension,
+        SURVEY.md 8f-1): returns a (B, 2) float64 tensor [sum |y - F(v)| * mask, sum mask], differentiable w.r.t. v
+        through column 0.  Needs an identity s_norm_func (every config of the reference uses s_normalize_none)."""
+        if self.normalize:
+            probe = torch.zeros(1)
+            if self.s_norm_func is not None and self.s_norm_func(probe) is not probe:
+                raise ValueError("rdfwi: the fused misfit needs an identity s_norm_func (s_normalize_none)")
+            v = self.v_denorm_func(v)
+        out = _WaveMisfit.apply(v, y, mask, self, bool(return_seismograms))
+        return out if return_seismograms else out[0]
+
+    def misfit(self, v, y, mask=None, return_seismograms=False):
+        """The reference's observation loss (core/losses.py:15-40) of the modelled data of `v` against `y`:
+        per-model mean |y - F(v)| over the observed samples (mask == 1; all samples when mask is None), shape (B,),
+        float32, differentiable w.r.t. v.  Equivalent to ``LossCalculator.observation_loss(op(v), y, mask)``."""
+        out = self.misfit_stats(v, y, mask, return_seismograms)
+        stats = out[0] if return_seismograms else out
+        loss = (stats[:, 0] / stats[:, 1].clamp(min=1.0)).to(torch.float32)
+        return (loss, out[1]) if return_seismograms else loss
 
     def pairs_per_gradient(self, B, nz, nx):
         """forward+adjoint cell-update pairs of one gradient evaluation."""

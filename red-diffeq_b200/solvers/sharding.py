@@ -58,6 +58,22 @@ class _SumGradAcrossRanks(torch.autograd.Function):
         return grad, None
 
 
+class _AllReduceSum(torch.autograd.Function):
+    """Sum over the ranks in the forward pass; identity in the backward pass (every rank holds the same replicated loss and
+    back-propagates it into its own work items only -- the per-rank velocity gradients meet in _SumGradAcrossRanks)."""
+
+    @staticmethod
+    def forward(ctx, t, group):
+        t = t.contiguous().clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad, None
+
+
 class ShardedFWIForward(nn.Module):
     """Multi-GPU front end of FWIForward (one process per GPU, torch.distributed already initialised).
 
@@ -110,6 +126,26 @@ class ShardedFWIForward(nn.Module):
             # nothing to do on this rank: a zero-size result that still lets backward() reach the all-reduce
             return v[:0].sum() * v.new_zeros((0, 0, 0, 0))
         return self._operator(shots)(v[models])
+
+    def misfit(self, v, y, mask=None):
+        """Shard-local data misfit: the reference's per-model observation loss
+        (core/losses.py:15-40) of the FULL observed data `y` (B, ns, nt, n_rec) [and mask], shape (B,), identical on
+        every rank.  Each rank runs its work items through the operator's fused ``misfit_stats`` (seismograms and
+        residuals never leave the GPU that modelled them), the (B, 2) partial sums are all-reduced (16 B per model), and
+        the normaliser is the global count.  ``loss.sum().backward()`` then leaves the full gradient on every rank after
+        the single all-reduce of d loss / d v."""
+        B = v.shape[0]
+        mode, models, shots = self.partition(B)
+        self.last_partition = (mode, models, shots)
+        v = _SumGradAcrossRanks.apply(v, self.group)
+        stats = torch.zeros((B, 2), dtype=torch.float64, device=v.device)
+        if len(shots) == 0 or models.stop <= models.start:
+            stats = stats + 0.0 * v.sum().to(torch.float64)  # idle rank: keeps backward() on the way to the all-reduce
+        else:
+            local = self._operator(shots).misfit_stats(v[models], self.local_slice(y), None if mask is None else self.local_slice(mask))
+            stats = torch.cat([stats[:models.start], local, stats[models.stop:]], dim=0)
+        stats = _AllReduceSum.apply(stats, self.group)
+        return (stats[:, 0] / stats[:, 1].clamp(min=1.0)).to(torch.float32)
 
     def local_slice(self, y):
         """The part of a (B, ns, nt, n_rec) tensor (observed data, masks) that matches forward()'s output."""

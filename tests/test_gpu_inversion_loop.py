@@ -41,3 +41,55 @@ def test_adam_loop_reduces_the_data_misfit():
     assert np.isfinite(losses).all()
     assert losses[-1] < 0.7 * losses[0], losses
     assert float(mu.grad[:, :, 0, :].abs().max()) == 0.0        # the padding ring gets no gradient from the data term
+
+
+def _setup(B=2, nz=20, nx=24):
+    from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize
+    from red_diffeq_b200.utils import synthetic
+    ctx = dict(n_grid=nx, nt=160, dx=10.0, dt=0.001, nbc=12, f=25.0, sz=10, gz=10, ng=nx, ns=3)
+    dev = torch.device("cuda:0")
+    op = FWIForward(ctx, dev, normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    mu_true_n = torch.tensor(synthetic.velocity_models(B, nz, nx, seed=21), device=dev)
+    with torch.no_grad():
+        y = op(mu_true_n)
+    mu_true = v_denormalize(mu_true_n)                      # the reference hands optimize() the model in m/s
+    mu0 = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(mu_true_n, (3, 3, 3, 3), mode="replicate"), 7, stride=1)
+    mu0 = torch.nn.functional.pad(mu0, (1, 1, 1, 1), value=0.0)
+    return op, mu0, mu_true, y
+
+
+@pytest.mark.parametrize("reg", [None, "tv"])
+def test_inversion_engine_variants_agree(reg):
+    """InversionEngine (core/inversion.py): operator + torch loss ops, fused misfit, and the CUDA-graphed iteration run the
+    same optimisation -- same losses per iteration, same final model (Adam amplifies last-bit differences a little)."""
+    from red_diffeq_b200 import InversionEngine
+    op, mu0, mu_true, y = _setup()
+    ts = 12
+    runs = {}
+    for name, kw in {"plain": dict(fused_misfit=False, cuda_graph=False), "fused": dict(fused_misfit=True, cuda_graph=False),
+                     "graph": dict(fused_misfit=True, cuda_graph=True)}.items():
+        eng = InversionEngine(regularization=reg, **kw)
+        mu, res = eng.optimize(mu0, mu_true, y, op, ts=ts, lr=0.03, reg_lambda=0.01, regularization=reg)
+        assert eng.used_cuda_graph == (name == "graph")
+        assert len(res) == 2 and all(len(res[0][k]) == ts for k in ("total_losses", "obs_losses", "reg_losses", "mae", "rmse", "ssim"))
+        runs[name] = (mu.detach().cpu().numpy(), np.array([res[i]["obs_losses"] for i in range(2)]),
+                      np.array([res[i]["mae"] for i in range(2)]))
+    base = runs["plain"]
+    assert np.isfinite(base[1]).all() and (base[1][:, -1] < 0.7 * base[1][:, 0]).all()
+    assert (base[2][:, -1] < base[2][:, 0]).all()                    # the model error shrinks too
+    for name in ("fused", "graph"):
+        np.testing.assert_allclose(runs[name][1], base[1], rtol=2e-3)
+        np.testing.assert_allclose(runs[name][0], base[0], atol=5e-3)
+        np.testing.assert_allclose(runs[name][2], base[2], rtol=2e-3)
+
+
+def test_inversion_engine_missing_traces_and_noise():
+    from red_diffeq_b200 import InversionEngine
+    op, mu0, mu_true, y = _setup()
+    torch.manual_seed(8888)
+    eng = InversionEngine(regularization="l2")            # cuda_graph automatic: on for the built-in regularisers
+    mu, res = eng.optimize(mu0, mu_true, y, op, ts=8, lr=0.03, reg_lambda=0.01, noise_std=1e-4, missing_number=5, regularization="l2")
+    assert eng.used_cuda_graph
+    assert mu.shape == (2, 1, 20, 24) and float(mu.abs().max()) <= 1.0
+    obs = np.array(res[0]["obs_losses"])
+    assert np.isfinite(obs).all() and obs[-1] < obs[0]

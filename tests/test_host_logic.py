@@ -49,7 +49,7 @@ def test_ctx_is_completed_in_place_like_the_reference():
 def test_cabi_exports_every_declared_symbol():
     from red_diffeq_b200 import _cabi
     header = open(os.path.join(ROOT, "include", "rdfwi.h")).read()
-    declared = sorted(set(re.findall(r"\b(rdfwi_[a-z_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(rdfwi_[a-z0-9_]+)\s*\(", header)))
     assert declared == sorted(_cabi.EXPORTS)
     lib = ctypes.CDLL(_cabi.LIB_PATH)      # loads on a CPU-only box (static cudart); no compute call is made
     for name in declared:

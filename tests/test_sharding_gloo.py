@@ -46,6 +46,13 @@ class _OracleOp(torch.nn.Module):
 
         return Fn.apply(v)
 
+    def misfit_stats(self, v, y, mask=None):
+        """Same contract as FWIForward.misfit_stats, composed from torch ops (the fused CUDA kernel needs a GPU)."""
+        seis = self.forward(v)
+        m = torch.ones_like(seis) if mask is None else mask.float()
+        dims = (1, 2, 3)
+        return torch.stack([((y - seis).abs() * m).sum(dim=dims).double(), m.sum(dim=dims).double()], dim=1)
+
 
 def _worker(rank, world, port, mode, B, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
@@ -85,3 +92,43 @@ def test_sharded_gradient_equals_single_process(tmp_path, mode, B, oracle):
     rel = np.linalg.norm(r0["grad"] - grad) / np.linalg.norm(grad)
     assert rel < 1e-5, rel
     assert int(r0["shape"][0]) * int(r0["shape"][1]) + int(r1["shape"][0]) * int(r1["shape"][1]) == B * CTX["ns"]
+
+
+def _misfit_worker(rank, world, port, mode, B, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from red_diffeq_b200.solvers.sharding import ShardedFWIForward
+    rng = np.random.default_rng(6)
+    v_np = (1500 + 3000 * rng.random((B, 1, NZ, NX))).astype(np.float32)
+    y_np = (1e-3 * rng.standard_normal((B, CTX["ns"], CTX["nt"], CTX["ng"]))).astype(np.float32)
+    mask_np = (rng.random(y_np.shape) > 0.3).astype(np.float32)
+    op = ShardedFWIForward(dict(CTX), "cpu", mode=mode, operator_factory=lambda ctx, dev, shot_subset=None: _OracleOp(ctx, dev, shot_subset))
+    v = torch.tensor(v_np, requires_grad=True)
+    loss = op.misfit(v, torch.tensor(y_np), torch.tensor(mask_np))
+    loss.sum().backward()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), grad=v.grad.numpy(), loss=loss.detach().numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,B", [("models", 3), ("shots", 1), ("shots", 2)])
+def test_sharded_misfit_equals_single_process(tmp_path, mode, B, oracle):
+    """Shard-local masked L1 misfit with the global normaliser: the (B,) loss and the gradient on every rank equal the
+    single-process LossCalculator.observation_loss semantics (reference core/losses.py:27-36) on the full data."""
+    port = 31500 + (os.getpid() + hash((mode, B))) % 2000
+    mp.spawn(_misfit_worker, args=(2, port, mode, B, str(tmp_path)), nprocs=2, join=True)
+    rng = np.random.default_rng(6)
+    v_np = (1500 + 3000 * rng.random((B, 1, NZ, NX))).astype(np.float32)
+    y_np = (1e-3 * rng.standard_normal((B, CTX["ns"], CTX["nt"], CTX["ng"]))).astype(np.float32)
+    mask_np = (rng.random(y_np.shape) > 0.3).astype(np.float32)
+    survey = oracle.Survey(dict(CTX), NZ, NX)
+    seis = oracle.forward(survey, v_np)
+    count = np.maximum(mask_np.sum(axis=(1, 2, 3)), 1.0)
+    loss = (np.abs(y_np - seis) * mask_np).sum(axis=(1, 2, 3), dtype=np.float64) / count
+    cot = (np.sign(seis - y_np) * mask_np / count[:, None, None, None]).astype(np.float32)
+    _, grad = oracle.gradient(survey, v_np, cot)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert np.array_equal(r0["grad"], r1["grad"]) and np.array_equal(r0["loss"], r1["loss"])
+    assert r0["loss"].shape == (B,) and np.allclose(r0["loss"], loss, rtol=1e-5)
+    rel = np.linalg.norm(r0["grad"] - grad) / np.linalg.norm(grad)
+    assert rel < 1e-5, rel

@@ -41,6 +41,11 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--reg", default="tv", choices=["none", "tv", "l2"])
     ap.add_argument("--workload", default="openfwi", choices=["openfwi", "marmousi"])
+    ap.add_argument("--fused-misfit", action="store_true", help="FWIForward.misfit instead of op(v) + torch loss ops")
+    ap.add_argument("--driver", default="loop", choices=["loop", "engine", "engine-graph"],
+                    help="loop = the reference's loop body restated here (host syncs included); engine = red_diffeq_b200."
+                         "InversionEngine (fused misfit, metrics fetched once); engine-graph = the same with the iteration "
+                         "captured in a CUDA graph")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     ctx = dict(synthetic.PDE_OPENFWI if args.workload == "openfwi" else synthetic.PDE_MARMOUSI)
@@ -53,14 +58,40 @@ def main():
     mask = torch.ones_like(y)
     mu0 = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(mu_true, (5, 5, 5, 5), mode="replicate"), 11, stride=1)
     mu = torch.nn.functional.pad(mu0, (1, 1, 1, 1), value=0.0).clone().requires_grad_(True)   # scripts/run_inversion.py:156
+    if args.driver != "loop":
+        import time
+        from red_diffeq_b200 import InversionEngine
+        reg = None if args.reg == "none" else args.reg
+        eng = InversionEngine(regularization=reg, fused_misfit=True, cuda_graph=args.driver == "engine-graph")
+        mu_true_phys = v_denormalize(mu_true)
+
+        def run(ts):   # wall clock around optimize(); fixed costs (warm-up, capture, the final fetch) cancel in the difference
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, res = eng.optimize(mu.detach(), mu_true_phys, y, op, ts=ts, lr=0.03, reg_lambda=0.01, regularization=reg)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, res
+        run(2)
+        t1, _ = run(args.iters)
+        t3, res = run(3 * args.iters)
+        s_iter = (t3 - t1) / (2 * args.iters)
+        pairs = op.pairs_per_gradient(B, nz, nx)
+        print(json.dumps({"metric": "s / inversion iteration", "value": s_iter, "workload": args.workload, "models": B,
+                          "regulariser": args.reg, "driver": args.driver, "cuda_graph": eng.used_cuda_graph,
+                          "iterations_timed": 2 * args.iters, "pairs_per_s_through_the_loop": pairs / s_iter,
+                          "misfit_first_last": [float(res[0]["obs_losses"][0]), float(res[0]["obs_losses"][-1])]}), flush=True)
+        return
     opt = torch.optim.Adam([mu], lr=0.03)
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=ts, eta_min=0.0)
     hist = {"total": [], "obs": [], "reg": [], "mae": [], "rmse": []}
 
     def iteration():
         x0 = mu + 1e-4 * torch.randn_like(mu)                                            # :73-74
-        pred = op(x0[:, :, 1:-1, 1:-1])                                                  # :78
-        loss_obs = ((y - pred).abs() * mask).sum(dim=(1, 2, 3)) / mask.sum(dim=(1, 2, 3)).clamp(min=1.0)
+        if args.fused_misfit:
+            loss_obs = op.misfit(x0[:, :, 1:-1, 1:-1], y, mask)
+        else:
+            pred = op(x0[:, :, 1:-1, 1:-1])                                              # :78
+            loss_obs = ((y - pred).abs() * mask).sum(dim=(1, 2, 3)) / mask.sum(dim=(1, 2, 3)).clamp(min=1.0)
         r = reg_loss(args.reg, x0)
         total = loss_obs + 0.01 * r
         opt.zero_grad(set_to_none=True)
@@ -104,7 +135,7 @@ def main():
     s_solver = e0.elapsed_time(e1) * 1e-3 / args.iters
     pairs = op.pairs_per_gradient(B, nz, nx)
     print(json.dumps({"metric": "s / inversion iteration", "value": s_iter, "workload": args.workload, "models": B,
-                      "regulariser": args.reg, "iterations_timed": args.iters, "solver_s_per_iter": s_solver,
+                      "regulariser": args.reg, "fused_misfit": args.fused_misfit, "iterations_timed": args.iters, "solver_s_per_iter": s_solver,
                       "solver_share": s_solver / s_iter, "pairs_per_s_through_the_loop": pairs / s_iter,
                       "misfit_first_last": [float(hist["obs"][0].mean()), float(hist["obs"][-1].mean())],
                       "mae_first_last": [float(hist["mae"][0].mean()), float(hist["mae"][-1].mean())]}), flush=True)
