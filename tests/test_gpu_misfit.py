@@ -92,4 +92,4 @@ def test_all_masked_model_has_zero_loss_and_gradient():
     vv = v.clone().requires_grad_(True)
     loss = op.misfit(vv, y, mask)
     loss.sum().backward()
-    assert float(loss[1]) == 0.0 and float(vv.grad[1].abs().max()) == 0.0 and float(vv.grad[0].abs().max()) > 0.0
+    assert float(loss[1].detach()) == 0.0 and float(vv.grad[1].abs().max()) == 0.0 and float(vv.grad[0].abs().max()) > 0.0

@@ -18,6 +18,8 @@ nz, nx = (70, 70) if kind == "openfwi" else (70, 190)
 dev = torch.device("cuda:0")
 vn = torch.tensor(synthetic.velocity_models(B, nz, nx), device=dev)
 configs = [(0, 0), (13, 0), (13, 8), (7, 0), (7, 16), (4, 0), (4, 16)]
+if len(sys.argv) > 3:   # "rows:cluster_size,..." e.g. 13:0,13:5,13:6
+    configs = [tuple(int(x) for x in c.split(":")) for c in sys.argv[3].split(",")]
 for rows, csize in configs:
     op = FWIForward(dict(ctx), dev, normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
     op.set_option("cluster_rows", rows)
@@ -34,7 +36,7 @@ for rows, csize in configs:
     plan = op._plan_for(nz, nx, dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     fwd = bwd = 0.0
-    reps = 5
+    reps = 5 if B < 16 else 2
     for _ in range(reps):
         v.grad = None
         ev[0].record()
