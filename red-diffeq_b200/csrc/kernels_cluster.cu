@@ -60,13 +60,24 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
         const float4 w4 = ld4(cb + (r + 2) * P);
         const float4 old = ld4(pb + r * P);
         const float kapz = kz[DIR * r];
-        // x-neighbours outside the float4 come from the adjacent lanes' centre vectors
-        float l2 = __shfl_up_sync(0xffffffffu, w2.z, 1);
-        float l1 = __shfl_up_sync(0xffffffffu, w2.w, 1);
-        float r0 = __shfl_down_sync(0xffffffffu, w2.x, 1);
-        float r1 = __shfl_down_sync(0xffffffffu, w2.y, 1);
-        if (th.edgeL) { l2 = eLp[r * P]; l1 = eLp[r * P + 1]; }
-        if (th.edgeR) { r0 = eRp[r * P]; r1 = eRp[r * P + 1]; }
+        float l2, l1, r0, r1;
+        if (PITCH > 0 && RMAX > 4) {
+            // (the 4-row few-shot configuration measured 10 % slower this way: it keeps the shuffles)
+            // production grids (even nxp, see the dispatcher): the two x-neighbour pairs are 8-byte aligned in the row that
+            // sits in shared memory anyway -- two LDS.64 per row for every lane, instead of four shuffles plus four
+            // predicated edge loads behind a divergent branch (ncu: BSSY/BSYNC stalls, ~18 of ~100 instructions per row)
+            const float2 lp = *reinterpret_cast<const float2 *>(eLp + r * P);
+            const float2 rp = *reinterpret_cast<const float2 *>(eRp + r * P);
+            l2 = lp.x; l1 = lp.y; r0 = rp.x; r1 = rp.y;
+        } else {
+            // generic pitch: x-neighbours outside the float4 come from the adjacent lanes' centre vectors
+            l2 = __shfl_up_sync(0xffffffffu, w2.z, 1);
+            l1 = __shfl_up_sync(0xffffffffu, w2.w, 1);
+            r0 = __shfl_down_sync(0xffffffffu, w2.x, 1);
+            r1 = __shfl_down_sync(0xffffffffu, w2.y, 1);
+            if (th.edgeL) { l2 = eLp[r * P]; l1 = eLp[r * P + 1]; }
+            if (th.edgeR) { r0 = eRp[r * P]; r1 = eRp[r * P + 1]; }
+        }
         const float e[8] = {l2, l1, w2.x, w2.y, w2.z, w2.w, r0, r1};
         float o[4];
         // Two cells per instruction for the twelve additions of a cell (FADD2, IEEE round-to-nearest per lane, same
@@ -509,7 +520,9 @@ template <int R>
 static cudaError_t dispatch_fwd_cluster_r(const Plan &p, const ClusterConfig &cc, const ClusterFwdArgs &a, cudaStream_t st, int *wave_only)
 {
     const bool adj = a.adj_mode != 0;
-    switch (p.g.pitch) {  // production grids get immediate row offsets (OpenFWI 310+2, Marmousi/Overthrust 430+2)
+    // production grids get immediate row offsets (OpenFWI 310+2, Marmousi/Overthrust 430+2); the specialised kernels read
+    // x-neighbour PAIRS from shared memory, which needs an even padded width
+    switch ((p.g.nxp & 1) == 0 ? p.g.pitch : 0) {
         case 312: return adj ? launch_fwd_cluster_t<R, 312, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 312, false, 512>(p, cc, a, st, wave_only);
         case 432: return adj ? launch_fwd_cluster_t<R, 432, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 432, false, 512>(p, cc, a, st, wave_only);
         default: return adj ? launch_fwd_cluster_t<R, 0, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 0, false, 512>(p, cc, a, st, wave_only);
@@ -521,7 +534,7 @@ static cudaError_t dispatch_fwd_cluster(const Plan &p, const ClusterConfig &cc, 
     const bool adj = a.adj_mode != 0;
     if (cc.nthreads == 256) {  // two CTAs per SM (experimental; OpenFWI pitch and runtime pitch only, 13 rows per thread)
         if (cc.rmax != kClusterRowsMax) return cudaErrorInvalidValue;
-        if (p.g.pitch == 312) return adj ? launch_fwd_cluster_t<kClusterRowsMax, 312, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<kClusterRowsMax, 312, false, 256>(p, cc, a, st, wave_only);
+        if (p.g.pitch == 312 && (p.g.nxp & 1) == 0) return adj ? launch_fwd_cluster_t<kClusterRowsMax, 312, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<kClusterRowsMax, 312, false, 256>(p, cc, a, st, wave_only);
         return adj ? launch_fwd_cluster_t<kClusterRowsMax, 0, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<kClusterRowsMax, 0, false, 256>(p, cc, a, st, wave_only);
     }
     switch (cc.rmax) {  // rows marched per thread: 13 for throughput, 7 / 4 on wider clusters when the shots are few
