@@ -92,3 +92,21 @@ def test_inversion_engine_missing_traces_and_noise():
     assert mu.shape == (2, 1, 20, 24) and float(mu.abs().max()) <= 1.0
     obs = np.array(res[0]["obs_losses"])
     assert np.isfinite(obs).all() and obs[-1] < obs[0]
+
+
+def test_files_in_files_out(tmp_path):
+    """tools/invert_family.py: .npy family (the reference's input format) -> InversionEngine -> per-model .npz with the
+    reference's keys; a short OpenFWI-shaped record so that it runs in seconds."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "invert_family.py"), "--synthetic", "3", "--batch", "2",
+                          "--ts", "6", "--nt", "300", "--out", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    info = json.loads(out.stdout.strip().splitlines()[-1])
+    assert info["models"] == 3 and info["cuda_graph"]
+    z = np.load(os.path.join(str(tmp_path), "results", "2_results.npz"))
+    assert z["result"].shape == (70, 70) and z["ground_truth"].shape == (70, 70) and z["obs_losses"].shape == (6,)
+    assert np.isfinite(z["obs_losses"]).all() and z["obs_losses"][-1] < z["obs_losses"][0]
