@@ -94,6 +94,7 @@ struct SweepThread {
     bool edgeL, edgeR;
     int eL, eR;               // column offsets of the (x-2, x-1) / (x+4, x+5) pairs, periodic
     bool colsp[4];
+    float mz[4];              // 0 in sponge columns (kappa follows the column profile), 1 elsewhere (row profile)
     int src_lr, rec_lr;
 };
 

@@ -53,6 +53,7 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
     const float *eRp = smem + cur + (2 + l0) * pitch + th.eR;
     const float *kz = smem + kap_off + l0;
     const float *push_dst = smem + prv + hp.dst + th.x;
+    const int nvalid = th.lb - th.la;
 
     float4 w0 = ld4(cb - 2 * P), w1 = ld4(cb - P), w2 = ld4(cb), w3 = ld4(cb + P);
 #pragma unroll
@@ -95,7 +96,9 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             // (((p1[z-1] + p1[z+1]) + p1[x-1]) + p1[x+1]) and the same at distance 2   (:79; + is commutative)
             const float2 s1 = f2add(f2add(f2add(up1, dn1), make_float2(e[j + 1], e[j + 2])), make_float2(e[j + 3], e[j + 4]));
             const float2 s2 = f2add(f2add(f2add(up2, dn2), make_float2(e[j], e[j + 1])), make_float2(e[j + 4], e[j + 5]));
-            const float2 kp = make_float2(th.colsp[j] ? kapx[j] : kapz, th.colsp[j + 1] ? kapx[j + 1] : kapz);
+            // kappa = column profile in sponge columns, row profile elsewhere (get_Abc: columns override rows): selected
+            // arithmetically -- 1 * kapz + 0 and 0 * kapz + kapx are exact -- so no predicate registers are tied up
+            const float2 kp = f2fma(make_float2(th.mz[j], th.mz[j + 1]), make_float2(kapz, kapz), make_float2(kapx[j], kapx[j + 1]));
             float2 res;
             if (EXACT) {  // forward wavefield: one rounding per reference op, products never packed (see above)
                 const float2 lap = f2add(make_float2(__fmul_rn(c2, s1.x), __fmul_rn(c2, s1.y)),
@@ -115,9 +118,8 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             }
             o[j] = res.x; o[j + 1] = res.y;
         }
-        const int lr = l0 + DIR * r;
         const float4 out = make_float4(o[0], o[1], o[2], o[3]);
-        if (lr >= th.la && lr < th.lb) st4(pb + r * P, out);
+        if (r < nvalid) st4(pb + r * P, out);  // marching rows 0 .. nvalid-1 are the thread's own (both directions)
         if (r < 2 && push_now) st_async_v4(push_dst + r * P, push_bar, hp.cta, out);  // edge rows leave at once
         w0 = w1; w1 = w2; w2 = w3; w3 = w4;
     }
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
     for (int j = 0; j < 4; ++j) {
         xc[j] = th.x + j >= g.nxp ? th.x + j - g.nxp : th.x + j;
         th.colsp[j] = sponge_index(xc[j], g.nxp, g.nbc) >= 0;
+        th.mz[j] = th.colsp[j] ? 0.0f : 1.0f;
     }
     // rows this thread must handle in the epilogue (local row index, or -1)
     th.src_lr = (g.isz - r0 >= th.la && g.isz - r0 < th.lb) ? g.isz - r0 : -1;
