@@ -48,12 +48,12 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the `ncu --set full`
 # capture of the same workload committed under profiles/ (None = not captured for this workload)
 NCU_TRAFFIC_BYTES = {
-    # per launch, from profiles/launches_r1_final_b64.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum on
+    # per launch, from profiles/launches_r1_v2_b64.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum on
     # the bench command): the forward launch writes the 123.7 GB history; each of the 5 adjoint-field launches writes a
     # 64-shot u history; each imaging launch reads both histories of its 64 shots
     ("openfwi_b64", "forward"): 123.8e9,
     ("openfwi_b64", "adjoint_field"): 24.7e9,
-    ("openfwi_b64", "imaging"): 52.2e9,      # profiles/ncu_imaging_r1_final_b64.txt (--set full): 52.11 GB read + 0.05 GB written
+    ("openfwi_b64", "imaging"): 52.0e9,      # profiles/launches_r1_v2_b64.csv: 51.9 GB read + 0.05 GB written per launch
     # fused cluster adjoint (adj_mode=1), profiles/ncu_adj_cluster_r1_full_b64.txt
     ("openfwi_b64", "adjoint_loop"): 124.13e9,
 }

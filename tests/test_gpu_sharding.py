@@ -44,3 +44,47 @@ def test_two_gpu_gradient_matches_reference(tmp_path, mode):
     g0, g1 = np.load(tmp_path / "grad0.npy"), np.load(tmp_path / "grad1.npy")
     assert np.array_equal(g0, g1)
     assert rel_l2(g0, g.grad_f32) <= 1e-4
+
+
+def _misfit_worker(rank, world, port, mode, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from red_diffeq_b200 import ShardedFWIForward, s_normalize_none, v_denormalize
+    g = Golden("tiny_half_receivers")
+    dev = torch.device("cuda", rank)
+    op = ShardedFWIForward(g.fresh_ctx(), dev, mode=mode, sample_temporal=g.sample_temporal, sample_spatial=g.sample_spatial,
+                           normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    rng = np.random.default_rng(3)
+    y = torch.tensor((1e-3 * rng.standard_normal((g.v.shape[0], 4, 70, 10))).astype(np.float32), device=dev)
+    mask = torch.tensor((rng.random((g.v.shape[0], 4, 70, 10)) > 0.25).astype(np.float32), device=dev)
+    v = torch.tensor(g.v, device=dev, requires_grad=True)
+    loss = op.misfit(v, y, mask)
+    loss.sum().backward()
+    torch.cuda.synchronize()
+    np.savez(os.path.join(out_dir, f"misfit{rank}.npz"), grad=v.grad.cpu().numpy(), loss=loss.detach().cpu().numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["models", "shots"])
+def test_two_gpu_sharded_misfit_matches_one_gpu(tmp_path, mode):
+    """Shard-local fused misfit over NCCL == the single-GPU fused misfit on the full data (loss per model and gradient)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize
+    g = Golden("tiny_half_receivers")
+    mp.spawn(_misfit_worker, args=(2, 29731 + (mode == "shots"), mode, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "misfit0.npz"), np.load(tmp_path / "misfit1.npz")
+    assert np.array_equal(r0["grad"], r1["grad"]) and np.array_equal(r0["loss"], r1["loss"])
+    op = FWIForward(g.fresh_ctx(), "cuda:0", sample_temporal=g.sample_temporal, sample_spatial=g.sample_spatial,
+                    normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    rng = np.random.default_rng(3)
+    y = torch.tensor((1e-3 * rng.standard_normal((g.v.shape[0], 4, 70, 10))).astype(np.float32), device="cuda:0")
+    mask = torch.tensor((rng.random((g.v.shape[0], 4, 70, 10)) > 0.25).astype(np.float32), device="cuda:0")
+    v = torch.tensor(g.v, device="cuda:0", requires_grad=True)
+    loss = op.misfit(v, y, mask)
+    loss.sum().backward()
+    assert np.allclose(r0["loss"], loss.detach().cpu().numpy(), rtol=1e-6)
+    assert rel_l2(r0["grad"], v.grad.cpu().numpy()) <= 1e-5
