@@ -37,7 +37,7 @@ def test_adam_loop_reduces_the_data_misfit():
         with torch.no_grad():
             mu.data.clamp_(-1, 1)
         sched.step()
-        losses.append(float(loss.sum()))
+        losses.append(float(loss.detach().sum()))
     assert np.isfinite(losses).all()
     assert losses[-1] < 0.7 * losses[0], losses
     assert float(mu.grad[:, :, 0, :].abs().max()) == 0.0        # the padding ring gets no gradient from the data term
