@@ -49,7 +49,7 @@ def run_case(n, ns, B, nt, peak):
     pairs = B * ns * (n + 240) ** 2 * nt
     rate = pairs / ((f_ms + a_ms) * 1e-3)
     seg = plan.get("history_segment")
-    eng_f = "cluster C=%d" % plan.get("cluster_size_used") if plan.get("cluster_size_used") and not seg and OPTS.get("engine") != 1 else "per-level"
+    eng_f = "cluster C=%d R=%d" % (plan.get("cluster_size_last"), plan.get("cluster_rows_last")) if plan.get("cluster_size_used") and not seg and OPTS.get("engine") != 1 else "per-level"
     sp = plan.get("adj_split")
     eng_a = {1: "cluster split", 2: "cluster split, forward recomputed", 3: "per-level split"}.get(sp) or \
         (("cluster fused C=%d" % plan.get("adj_cluster_size_used")) if plan.get("adj_cluster_size_used") and not seg and OPTS.get("engine") != 1 else "per-level fused")
