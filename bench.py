@@ -364,8 +364,12 @@ def main():
         for kk in kernels.values():
             kk["achieved_gbs"] = kk["algo_bytes"] / (kk["us"] * 1e-6) / 1e9 if kk["us"] > 0 else None
             kk["avg_launch_us"] = kk["us"] / max(kk["launches"], 1)
-        for kk in kernels.values():
+        for name, kk in kernels.items():
             kk["frac"] = kk["achieved_gbs"] / peak if kk["achieved_gbs"] else None
+            # what really crossed the HBM pins (ncu dram bytes of one launch x launches), where a capture exists: the
+            # cluster-resident kernels move far less than their algorithmic bytes, the imaging kernel exactly its own
+            tb = NCU_TRAFFIC_BYTES.get((args.workload, name))
+            kk["dram_gbs"] = tb * kk["launches"] / (kk["us"] * 1e-6) / 1e9 if tb and kk["us"] > 0 else None
         dom_key = max(kernels, key=lambda q: kernels[q]["us"])
         dom = kernels[dom_key]
         fwd_achieved = ALGO_BYTES_FWD * cell_updates / (fwd_ms * 1e-3) / 1e9
@@ -391,13 +395,16 @@ def main():
                     "d2h_bytes_per_step": int(grad_host.numel() * 4 + loss_host.numel() * 4)},
             "gpu_launches": int((launches_f + launches_b) * args.steps),
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": dom["frac"], "traffic": NCU_TRAFFIC_BYTES.get((args.workload, dom_key)),
+                         "frac": dom["frac"], "frac_of_nominal_8TBs": dom["achieved_gbs"] / 8000.0 if dom["achieved_gbs"] else None,
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, dom_key)),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algo_bytes"] / max(dom["launches"], 1),
                          "avg_launch_us": dom["avg_launch_us"], "launches_per_step": dom["launches"],
                          "share_of_step": dom["us"] * 1e-3 / ms_per_step,
                          "kernels": {k: {"kernel": v["kernel"], "ms_per_step": v["us"] * 1e-3, "launches_per_step": v["launches"],
                                          "algorithmic_GB_per_step": v["algo_bytes"] / 1e9, "achieved_gbs": v["achieved_gbs"],
-                                         "frac": v["frac"], "traffic": NCU_TRAFFIC_BYTES.get((args.workload, k))}
+                                         "frac": v["frac"], "traffic": NCU_TRAFFIC_BYTES.get((args.workload, k)),
+                                         "measured_dram_gbs": v["dram_gbs"],
+                                         "measured_dram_frac": v["dram_gbs"] / peak if v["dram_gbs"] else None}
                                      for k, v in kernels.items()},
                          # SURVEY.md 8(d) aggregates: 12 B forward, 16 B adjoint (both adjoint kernels together), 28 B pair
                          "forward_frac": fwd_achieved / peak, "adjoint_frac": adj_achieved / peak,
