@@ -102,7 +102,9 @@ class InversionEngine:
         mask = trace_mask if mask is None else mask.to(device) * trace_mask
         y, mask = y.contiguous().float(), mask.contiguous().float()
         noise_x0 = regularization == "diffusion"                                     # :71-76
-        use_graph = (builtin if self.cuda_graph is None else bool(self.cuda_graph)) and device.type == "cuda"
+        fused = self.fused_misfit and hasattr(fwi_forward, "misfit")   # any other callable operator: torch loss ops
+        multi_rank = getattr(fwi_forward, "world_size", 1) > 1            # sharded operator: collectives stay out of graphs
+        use_graph = (builtin and not multi_rank if self.cuda_graph is None else bool(self.cuda_graph)) and device.type == "cuda"
 
         lr_t = torch.tensor(float(lr), device=device)
         step_t = torch.zeros(1, dtype=torch.long, device=device)
@@ -113,7 +115,7 @@ class InversionEngine:
 
         def iteration():
             x0_pred = mu + self.sigma_x0 * torch.randn_like(mu) if noise_x0 else mu
-            if self.fused_misfit:
+            if fused:
                 loss_obs = fwi_forward.misfit(x0_pred[:, :, 1:-1, 1:-1], y, mask)
             else:
                 pred = fwi_forward(x0_pred[:, :, 1:-1, 1:-1])                         # :78-79, losses.py:27-36

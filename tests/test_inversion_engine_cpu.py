@@ -108,6 +108,6 @@ def test_user_regulariser_with_time_tensor():
         calls.append(mu.shape)
         return (mu ** 2).mean(dim=(1, 2, 3)), torch.zeros(2, dtype=torch.long)
 
-    engine = InversionEngine(regularization="diffusion", regularizer=reg, fused_misfit=False)
+    engine = InversionEngine(regularization="diffusion", regularizer=reg)   # operator without .misfit: torch loss ops
     mu, res = engine.optimize(torch.zeros(2, 1, 8, 10), mu_true, y, op, ts=4, regularization="diffusion")
     assert len(calls) == 4 and calls[0] == (2, 1, 8, 10) and np.isfinite(res[1]["reg_losses"]).all()

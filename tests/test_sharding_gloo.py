@@ -20,8 +20,9 @@ NZ, NX = 12, 16
 class _OracleOp(torch.nn.Module):
     """FWIForward-shaped stand-in: forward + adjoint through the CPU oracle (physical velocities in, no normalisation)."""
 
-    def __init__(self, ctx, device, shot_subset=None):
+    def __init__(self, ctx, device, shot_subset=None, normalize=False):
         super().__init__()
+        self.normalize, self.device = normalize, torch.device("cpu")
         from oracle import fwi_oracle
         ctx = dict(ctx)
         if shot_subset is not None:  # sources of this shard, in grid units like a user-supplied ctx['sx']
@@ -31,6 +32,8 @@ class _OracleOp(torch.nn.Module):
 
     def forward(self, v):
         oracle, survey = self.oracle, self.survey
+        if self.normalize:   # [-1, 1] -> m/s like the product operator with v_denormalize
+            v = (v + 1) / 2 * 3000 + 1500
 
         class Fn(torch.autograd.Function):
             @staticmethod
@@ -132,3 +135,44 @@ def test_sharded_misfit_equals_single_process(tmp_path, mode, B, oracle):
     assert r0["loss"].shape == (B,) and np.allclose(r0["loss"], loss, rtol=1e-5)
     rel = np.linalg.norm(r0["grad"] - grad) / np.linalg.norm(grad)
     assert rel < 1e-5, rel
+
+
+def _engine_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mu, res = _run_engine()
+    np.savez(os.path.join(out_dir, f"engine{rank}.npz"), mu=mu, obs=res)
+    dist.destroy_process_group()
+
+
+def _run_engine():
+    """InversionEngine around a ShardedFWIForward (oracle-backed stand-in operators): shard-local misfit, one gradient
+    all-reduce per iteration, Adam on the replicated leaf."""
+    from red_diffeq_b200 import InversionEngine
+    from red_diffeq_b200.solvers.sharding import ShardedFWIForward
+    rng = np.random.default_rng(9)
+    B = 2
+    mu_true_n = (0.6 * rng.random((B, 1, NZ, NX)) - 0.3).astype(np.float32)
+    op = ShardedFWIForward(dict(CTX), "cpu", mode="shots",
+                           operator_factory=lambda ctx, dev, shot_subset=None: _OracleOp(ctx, dev, shot_subset, normalize=True))
+    full = _OracleOp(dict(CTX), "cpu", None, normalize=True)
+    with torch.no_grad():
+        y = full(torch.tensor(mu_true_n))
+    mu0 = torch.nn.functional.pad(torch.zeros(B, 1, NZ, NX), (1, 1, 1, 1))
+    mu_true = (torch.tensor(mu_true_n) + 1) / 2 * 3000 + 1500
+    eng = InversionEngine(regularization="tv")
+    mu, res = eng.optimize(mu0, mu_true, y, op, ts=4, lr=0.03, reg_lambda=0.01, regularization="tv")
+    assert not eng.used_cuda_graph
+    return mu.detach().numpy(), np.array([r["obs_losses"] for r in res])
+
+
+def test_inversion_engine_on_a_sharded_operator(tmp_path, oracle):
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_engine_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "engine0.npz"), np.load(tmp_path / "engine1.npz")
+    assert np.array_equal(r0["mu"], r1["mu"]) and np.array_equal(r0["obs"], r1["obs"])      # replicas stay in lock-step
+    mu_single, obs_single = _run_engine()                                                   # world size 1, same code
+    assert np.allclose(r0["obs"], obs_single, rtol=5e-4)          # Adam amplifies the different summation order a little
+    assert np.allclose(r0["mu"], mu_single, atol=2e-3)
+    assert (obs_single[:, -1] < obs_single[:, 0]).all()
