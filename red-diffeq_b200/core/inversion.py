@@ -17,9 +17,11 @@ What is different from the reference's loop (none of it changes the mathematics)
     Adam runs with ``capturable=True`` and the cosine schedule (CosineAnnealingLR with eta_min = 0 in closed form,
     lr_k = lr/2 (1 + cos(pi k / ts))) lives in a device scalar.
 
-The diffusion regulariser (regularization/diffusion.py, a stock-PyTorch U-Net) is out of this repository's scope: pass it
-as ``regularizer=RegularizationMethod('diffusion', model).get_reg_loss`` (any callable mu -> reg_loss (B,) or
-(reg_loss, time_tensor)); 'tv' and 'l2' (regularization/benchmark.py:4-37) are restated here because they are five lines.
+The denoiser of the diffusion regulariser (a stock-PyTorch U-Net) is out of this repository's scope: hand the reference's
+GaussianDiffusion object to the constructor (``InversionEngine(diffusion_model, ...)``, as the reference does) and
+regularization='diffusion' calls it through ``regularization.diffusion.REDDiffEq`` (no_grad, batched patches); or pass any
+callable mu -> reg_loss (B,) or (reg_loss, time_tensor) as ``regularizer``.  'tv' and 'l2' (regularization/benchmark.py:4-37)
+are restated here because they are five lines.
 """
 import math
 
@@ -55,6 +57,11 @@ class InversionEngine:
         self.diffusion_model = diffusion_model
         self.ssim_loss = ssim_loss
         self.regularization = regularization
+        if regularizer is None and diffusion_model is not None:   # like the reference's RegularizationMethod('diffusion', model)
+            from ..regularization.diffusion import REDDiffEq
+            self._red = REDDiffEq(diffusion_model, use_time_weight=use_time_weight, sigma_x0=sigma_x0, fixed_timestep=fixed_timestep)
+        else:
+            self._red = None
         self.regularizer = regularizer
         self.sigma_x0 = sigma_x0
         self.fused_misfit = fused_misfit
@@ -68,6 +75,8 @@ class InversionEngine:
             raise ValueError(f"Unknown regularization: {regularization}")          # core/inversion.py:32-33
         if self.regularizer is not None:
             fn, builtin = self.regularizer, False
+        elif regularization == "diffusion" and self._red is not None:
+            fn, builtin = self._red, False   # stock-PyTorch denoiser, called under no_grad with batched patches
         elif regularization == "tv":
             fn, builtin = total_variation_loss, True
         elif regularization == "l2":
