@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
     float *s_raw = s_cot + 2 * g.nxp;  // [2][nrec] cotangent rows as they sit in HBM, landed by cp.async (adjoint mode)
     float *s_wav = s_raw + 2 * g.nrec;
     const bool wav_in_smem = a.wav_smem != 0;
+    const bool st1 = a.st == 1;  // every level is sampled (all configs of the reference): no integer division on the level's critical path
 
     const int tid = threadIdx.x, lane_id = tid & 31;
     const int grp = tid / g.q4, col = tid - grp * g.q4;
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
         // the way waits for an HBM round trip: fetched by dependent loads, the row cost ~10 000 cycles per level on
         // Marmousi-width grids -- more than the sweep (tools/trace_levels.py).
         auto fetch_cot = [&](const int tr, const int buf) {
-            if (tr < 0 || tr % a.st != 0) return;
-            const float *gt = a.cot + ((size_t)gshot * g.nt_out + tr / a.st) * g.nrec;
+            if (tr < 0 || (!st1 && tr % a.st != 0)) return;
+            const float *gt = a.cot + ((size_t)gshot * g.nt_out + (st1 ? tr : tr / a.st)) * g.nrec;
             float *dst = s_raw + buf * g.nrec;
             for (int r = lane_id; r < g.nrec; r += 32)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + r)), "l"(gt + r) : "memory");
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
         auto sum_cot = [&](const int tr, const int buf) {
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
-            if (tr < 0 || tr % a.st != 0) return;
+            if (tr < 0 || (!st1 && tr % a.st != 0)) return;
             const float *raw = s_raw + buf * g.nrec;
             float *dst = s_cot + buf * g.nxp;
 #pragma unroll 4
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
                 else fwd_sweep<RMAX, PITCH, 1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
                 stamp(t, 2);
                 if (ADJ) {
-                    if (th.rec_lr >= 0 && trev % a.st == 0) {  // u_t[rec] += alpha * g_t  (adjoint of the gather, :83)
+                    if (th.rec_lr >= 0 && (st1 || trev % a.st == 0)) {  // u_t[rec] += alpha * g_t  (adjoint of the gather, :83)
                         float4 v = ld4(smem + p0 + th.rec_lr * pitch);
                         const float *cc = s_cot + (t & 1) * g.nxp;
                         v.x += al_rec.x * cc[xc[0]]; v.y += al_rec.y * cc[xc[1]]; v.z += al_rec.z * cc[xc[2]]; v.w += al_rec.w * cc[xc[3]];
@@ -387,8 +388,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
             // usually owns no rows -- from the finished level while the other warps already sweep the next one (that
             // buffer is read-only until the barrier after next).  In the owner threads' epilogue it sat on the critical
             // path of the whole cluster: ~1900 of 9000 cycles per level (tools/trace_levels.py).
-            if (!ADJ && a.seis != nullptr && tid >= NT - 32 && t % a.st == 0 && g.igz >= r0 && g.igz < r0 + nrows) {
-                float *seis_t = a.seis + ((size_t)gshot * g.nt_out + t / a.st) * g.nrec;
+            if (!ADJ && a.seis != nullptr && tid >= NT - 32 && (st1 || t % a.st == 0) && g.igz >= r0 && g.igz < r0 + nrows) {
+                float *seis_t = a.seis + ((size_t)gshot * g.nt_out + (st1 ? t : t / a.st)) * g.nrec;
                 const float *row = smem + prv + (2 + g.igz - r0) * pitch;
                 for (int xx = lane_id; xx < g.nxp; xx += 32)
                     for (int k = s_rec_ptr[xx]; k < s_rec_ptr[xx + 1]; ++k) seis_t[s_rec_idx[k]] = row[xx];
