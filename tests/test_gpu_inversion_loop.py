@@ -89,7 +89,7 @@ def test_inversion_engine_missing_traces_and_noise():
     eng = InversionEngine(regularization="l2")            # cuda_graph automatic: on for the built-in regularisers
     mu, res = eng.optimize(mu0, mu_true, y, op, ts=8, lr=0.03, reg_lambda=0.01, noise_std=1e-4, missing_number=5, regularization="l2")
     assert eng.used_cuda_graph
-    assert mu.shape == (2, 1, 20, 24) and float(mu.abs().max()) <= 1.0
+    assert mu.shape == (2, 1, 20, 24) and float(mu.detach().abs().max()) <= 1.0
     obs = np.array(res[0]["obs_losses"])
     assert np.isfinite(obs).all() and obs[-1] < obs[0]
 
