@@ -269,10 +269,18 @@ def main():
         e2.record()
         return e0, e1, e2, launches_f, op.last_launches - launches_f
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def step_e2e():
+        # the observed data (90 MB for the headline batch) are not needed before the misfit: their host -> device copy runs
+        # on a second stream, inside the timed region, while the forward kernel is busy; the velocity batch goes first
         v = vn_host.to(dev, non_blocking=True).requires_grad_(True)
-        y = y_host.to(dev, non_blocking=True)
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(copy_stream):
+            y = y_host.to(dev, non_blocking=True)
         seis = fwd(v)
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
+        y.record_stream(torch.cuda.current_stream(dev))
         loss = (seis - y).abs().mean(dim=(1, 2, 3))          # the reference's L1 data misfit (core/losses.py:27-41)
         loss.sum().backward()
         grad_host.copy_(v.grad, non_blocking=True)
