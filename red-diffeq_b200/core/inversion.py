@@ -24,6 +24,7 @@ callable mu -> reg_loss (B,) or (reg_loss, time_tensor) as ``regularizer``.  'tv
 are restated here because they are five lines.
 """
 import math
+import time
 
 import torch
 
@@ -67,7 +68,14 @@ class InversionEngine:
         self.fused_misfit = fused_misfit
         self.cuda_graph = cuda_graph
         self.used_cuda_graph = False
+        self.last_loop_seconds = None
         self.device = getattr(diffusion_model, "device", None)
+
+    @staticmethod
+    def _tick(device):
+        if device.type == "cuda":
+            torch.cuda.synchronize(device)
+        return time.perf_counter()
 
     # ------------------------------------------------------------------------------------------
     def _resolve_regularizer(self, regularization):
@@ -179,11 +187,14 @@ class InversionEngine:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):   # records one iteration; nothing runs yet
                 iteration()
+            t0 = self._tick(device)
             for _ in range(ts):
                 graph.replay()
         else:
+            t0 = self._tick(device)
             for _ in range(ts):
                 iteration()
+        self.last_loop_seconds = self._tick(device) - t0   # the ts iterations alone (no warm-up, capture or result fetch)
 
         fetched = {k: h.cpu().numpy() for k, h in hist.items()}                       # the ONE device -> host transfer
         final_results_per_model = [{k: [fetched[k][t][i] for t in range(ts)] for k in names} for i in range(B)]   # :115-126
