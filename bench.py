@@ -131,6 +131,12 @@ def cpu_baseline(ctx, nz, nx, target_seconds=20.0):
     from oracle import build_oracle, fwi_oracle
     from red_diffeq_b200.utils import synthetic
     build_oracle.build()
+    # all the host cores this process may use: launchers such as torchrun export OMP_NUM_THREADS=1 to their workers, which
+    # would time the CPU arm on one thread at N > 1
+    try:
+        fwi_oracle.set_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        fwi_oracle.set_threads(os.cpu_count() or 1)
     threads = fwi_oracle.threads()
     sv = fwi_oracle.Survey(dict(ctx), nz, nx)
     B = max(1, -(-threads // sv.ns))          # one shot per host thread

@@ -30,3 +30,4 @@ int fwi_oracle_coeffs_f32(const fwi_oracle_geom *g, const float *v, float *plane
 }
 
 int fwi_oracle_threads(void) { return omp_get_max_threads(); }
+void fwi_oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }

@@ -37,6 +37,8 @@ int fwi_oracle_gradient_f64(const fwi_oracle_geom *g, const double *v, const dou
 /* coefficient planes of model b=0 only: alpha, kappa, temp1, temp2, beta_dt (each nzp*nxp) */
 int fwi_oracle_coeffs_f32(const fwi_oracle_geom *g, const float *v, float *planes5, float *velmin, int *argmin);
 int fwi_oracle_threads(void);
+/* OpenMP threads of the following calls (bench.py: launchers such as torchrun export OMP_NUM_THREADS=1) */
+void fwi_oracle_set_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,11 @@ def threads() -> int:
     return int(_lib().fwi_oracle_threads())
 
 
+def set_threads(n: int) -> None:
+    """OpenMP threads used by the following calls (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    _lib().fwi_oracle_set_threads(int(n))
+
+
 def ricker_wavelet(f, dt, nt):
     """Zero-phase Ricker, float64, zero-padded to nt (solvers/pde.py:26-36).
 
