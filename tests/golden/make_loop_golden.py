@@ -69,6 +69,12 @@ def main():
     data["pert/y"], data["pert/missing"], data["pert/mask"] = y.numpy(), ym.numpy(), mask.numpy()
     data["pert/gauss"] = dt.add_noise_to_seismic(y, 0.3, "gaussian", generator=torch.Generator().manual_seed(3)).numpy()
     data["pert/laplace"] = dt.add_noise_to_seismic(y, 0.3, "laplace", generator=torch.Generator().manual_seed(3)).numpy()
+    # initial models (utils/data_trans.py:66-102)
+    v = 1500 + 3000 * torch.rand(1, 1, 14, 18, generator=torch.Generator().manual_seed(4))
+    data["init/v"] = v.numpy()
+    data["init/smoothed"] = dt.prepare_initial_model(v, "smoothed", sigma=3.0).numpy()
+    data["init/homogeneous"] = dt.prepare_initial_model(v, "homogeneous").numpy()
+    data["init/linear"] = dt.prepare_initial_model(v, "linear").numpy()
     np.savez_compressed(os.path.join(HERE, "loop_toy.npz"), **data)
     print("wrote loop_toy.npz with", len(data), "arrays")
 

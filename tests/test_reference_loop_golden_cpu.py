@@ -53,3 +53,11 @@ def test_data_perturbations_reproduce_the_reference_functions(fx):
     assert np.array_equal(g.numpy(), fx["pert/gauss"])
     lap = add_noise_to_seismic(y, 0.3, "laplace", generator=torch.Generator().manual_seed(3))
     assert np.allclose(lap.numpy(), fx["pert/laplace"], rtol=1e-5, atol=1e-7)
+
+
+def test_initial_models_reproduce_the_reference_function(fx):
+    from red_diffeq_b200.utils.io import prepare_initial_model
+    v = torch.tensor(fx["init/v"])
+    assert np.array_equal(prepare_initial_model(v, "smoothed", sigma=3.0).numpy(), fx["init/smoothed"])
+    assert np.array_equal(prepare_initial_model(v, "homogeneous").numpy(), fx["init/homogeneous"])
+    assert np.array_equal(prepare_initial_model(v, "linear").numpy(), fx["init/linear"])
