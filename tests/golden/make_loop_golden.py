@@ -69,6 +69,21 @@ def main():
     data["pert/y"], data["pert/missing"], data["pert/mask"] = y.numpy(), ym.numpy(), mask.numpy()
     data["pert/gauss"] = dt.add_noise_to_seismic(y, 0.3, "gaussian", generator=torch.Generator().manual_seed(3)).numpy()
     data["pert/laplace"] = dt.add_noise_to_seismic(y, 0.3, "laplace", generator=torch.Generator().manual_seed(3)).numpy()
+    # observation loss (core/losses.py:15-40) and its gradient w.r.t. the predicted data, masked and unmasked
+    losses = importlib.import_module("red_diffeq.core.losses")
+    calc = losses.LossCalculator(None)
+    g = torch.Generator().manual_seed(6)
+    pred = (1e-3 * torch.randn(2, 3, 130, 16, generator=g)).requires_grad_(True)
+    target = 1e-3 * torch.randn(2, 3, 130, 16, generator=g)
+    target[0, 0, :5] = pred.detach()[0, 0, :5]          # exact ties: sign(0) = 0
+    mask = (torch.rand(2, 3, 130, 16, generator=g) > 0.3).float()
+    weights = torch.tensor([1.0, 1.7])
+    data["loss/pred"], data["loss/target"], data["loss/mask"] = pred.detach().numpy(), target.numpy(), mask.numpy()
+    for tag, m in (("masked", mask), ("plain", None)):
+        pred.grad = None
+        loss = calc.observation_loss(pred, target, mask=m)
+        (loss * weights).sum().backward()
+        data[f"loss/{tag}_loss"], data[f"loss/{tag}_grad"] = loss.detach().numpy(), pred.grad.numpy().copy()
     # initial models (utils/data_trans.py:66-102)
     v = 1500 + 3000 * torch.rand(1, 1, 14, 18, generator=torch.Generator().manual_seed(4))
     data["init/v"] = v.numpy()

@@ -93,3 +93,32 @@ def test_all_masked_model_has_zero_loss_and_gradient():
     loss = op.misfit(vv, y, mask)
     loss.sum().backward()
     assert float(loss[1].detach()) == 0.0 and float(vv.grad[1].abs().max()) == 0.0 and float(vv.grad[0].abs().max()) > 0.0
+
+
+@pytest.mark.parametrize("tag", ["masked", "plain"])
+def test_misfit_kernel_reproduces_the_reference_loss_calculator(tag):
+    """rdfwi_misfit_l1 called through the C ABI on recorded inputs against the outputs of the reference's own
+    LossCalculator.observation_loss and its autograd (tests/golden/loop_toy.npz, written by tests/golden/make_loop_golden.py):
+    per-model loss, and d(sum_b w_b loss_b)/d predicted = w_b / count_b * sign field, exact ties included."""
+    import os
+    from conftest import GOLDEN_DIR
+    fx = np.load(os.path.join(GOLDEN_DIR, "loop_toy.npz"))
+    g = Golden("tiny_default")                       # survey with (ns, nt_out, nrec) = (3, 130, 16)
+    op = _op(g)
+    plan = op._plan_for(g.v.shape[2], g.v.shape[3], torch.device("cuda:0"))
+    seis = torch.tensor(fx["loss/pred"], device="cuda:0")
+    obs = torch.tensor(fx["loss/target"], device="cuda:0")
+    mask = torch.tensor(fx["loss/mask"], device="cuda:0") if tag == "masked" else None
+    B = seis.shape[0]
+    stats = torch.empty((B, 2), dtype=torch.float64, device="cuda:0")
+    sign = torch.empty_like(seis)
+    ws = torch.empty(plan.workspace_bytes(B), dtype=torch.uint8, device="cuda:0")
+    plan.misfit_l1(seis.data_ptr(), obs.data_ptr(), mask.data_ptr() if mask is not None else None, B, stats.data_ptr(),
+                   sign.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    loss = (stats[:, 0] / stats[:, 1].clamp(min=1.0)).float().cpu().numpy()
+    assert np.allclose(loss, fx[f"loss/{tag}_loss"], rtol=2e-6, atol=0)
+    w = torch.tensor([1.0, 1.7], device="cuda:0", dtype=torch.float64)
+    grad = (sign * (w / stats[:, 1].clamp(min=1.0)).float().view(B, 1, 1, 1)).cpu().numpy()
+    assert np.allclose(grad, fx[f"loss/{tag}_grad"], rtol=1e-6, atol=0)
+    assert np.array_equal(grad == 0, fx[f"loss/{tag}_grad"] == 0)        # masked samples and exact ties carry no gradient
