@@ -84,6 +84,15 @@ def main():
         loss = calc.observation_loss(pred, target, mask=m)
         (loss * weights).sum().backward()
         data[f"loss/{tag}_loss"], data[f"loss/{tag}_grad"] = loss.detach().numpy(), pred.grad.numpy().copy()
+    # patch layout (regularization/diffusion.py:7-27) over a range of widths / heights
+    cp = mods["red_diffeq.regularization.diffusion"].calculate_patches
+    rows = []
+    for h in (10, 70, 72):
+        for w in list(range(h, 4 * h + 3, 7)) + [190, 430]:
+            spans, overlaps = cp(w, h)
+            rows.append([w, h, len(spans)] + [v for s in spans for v in s] + overlaps + [-1] * (3 * 8 - 1 - 3 * len(spans) + 1))
+    width = max(len(r) for r in rows)
+    data["patches/table"] = np.array([r + [-1] * (width - len(r)) for r in rows], dtype=np.int64)
     # initial models (utils/data_trans.py:66-102)
     v = 1500 + 3000 * torch.rand(1, 1, 14, 18, generator=torch.Generator().manual_seed(4))
     data["init/v"] = v.numpy()

@@ -61,3 +61,13 @@ def test_initial_models_reproduce_the_reference_function(fx):
     assert np.array_equal(prepare_initial_model(v, "smoothed", sigma=3.0).numpy(), fx["init/smoothed"])
     assert np.array_equal(prepare_initial_model(v, "homogeneous").numpy(), fx["init/homogeneous"])
     assert np.array_equal(prepare_initial_model(v, "linear").numpy(), fx["init/linear"])
+
+
+def test_patch_layout_reproduces_the_reference_function(fx):
+    from red_diffeq_b200.regularization import calculate_patches
+    for row in fx["patches/table"]:
+        w, h, k = (int(v) for v in row[:3])
+        spans, overlaps = calculate_patches(w, h)
+        assert len(spans) == k
+        flat = [v for s in spans for v in s] + list(overlaps)
+        assert flat == [int(v) for v in row[3:3 + len(flat)]], (w, h)
