@@ -394,3 +394,26 @@ def test_full_size_batch_properties():
         assert torch.equal(vb.grad, g1[b:b + 1])
     op.release_memory()
     solo.release_memory()
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """examples/c_abi_example.c: the library used from plain C (no Python, no torch) -- forward + adjoint run and return a
+    finite, non-zero gradient."""
+    import os
+    import re
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    from red_diffeq_b200 import _cabi
+    cudart = "/usr/local/cuda/lib64"
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cudart, "libcudart.so")):
+        pytest.skip("needs gcc and the CUDA runtime")
+    exe = str(tmp_path / "rdfwi_example")
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_example.c"),
+                           "-o", exe, "-L", libdir, "-lrdfwi", "-L", cudart, "-lcudart", "-lm",
+                           "-Wl,-rpath," + libdir, "-Wl,-rpath," + cudart])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    m = re.search(r"= ([0-9.e+-]+), kernel launches of the adjoint pass: (\d+)", out.stdout)
+    assert m and np.isfinite(float(m.group(1))) and float(m.group(1)) > 0 and int(m.group(2)) > 3, out.stdout

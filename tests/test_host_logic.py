@@ -94,3 +94,21 @@ def test_partition_plans():
     assert shots_seen == list(range(40))
     with pytest.raises(ValueError):
         plan_partition(1, 5, 2, 0, mode="rows")
+
+
+def test_c_example_compiles_and_links_against_the_library(tmp_path):
+    """include/rdfwi.h is valid C99 and the plain-C example of the ABI (examples/c_abi_example.c: plan, forward, adjoint with
+    caller-owned buffers, no Python / torch) links against librdfwi.so; it is run on the GPU by tests/test_gpu_parity.py."""
+    import shutil
+    import subprocess
+    from red_diffeq_b200 import _cabi
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    obj = str(tmp_path / "example.o")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c",
+                           os.path.join(ROOT, "examples", "c_abi_example.c"), "-o", obj])
+    cudart = "/usr/local/cuda/lib64"
+    if not os.path.exists(os.path.join(cudart, "libcudart.so")):
+        pytest.skip("no CUDA runtime to link the example's cudaMalloc / cudaMemcpy against")
+    subprocess.check_call(["gcc", obj, "-o", str(tmp_path / "example"), "-L", os.path.dirname(_cabi.LIB_PATH), "-lrdfwi",
+                           "-L", cudart, "-lcudart", "-lm"])
