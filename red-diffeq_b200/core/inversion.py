@@ -95,15 +95,21 @@ class InversionEngine:
             raise ValueError(f"regularization={regularization!r} runs on the stock PyTorch path: pass the reference's "
                              "RegularizationMethod(...).get_reg_loss as `regularizer`")
 
-        def call(mu):
-            out = fn(mu)
+        takes_generator = fn is self._red and fn is not None   # REDDiffEq draws its timesteps / noise from a generator
+
+        def call(mu, generator=None):
+            out = fn(mu, generator=generator) if takes_generator else fn(mu)
             return out[0] if isinstance(out, tuple) else out
+        call.takes_generator = takes_generator
         return call, builtin
 
     def optimize(self, mu, mu_true, y, fwi_forward, ts=300, lr=0.03, reg_lambda=0.01, noise_std=0.0,
                  noise_type="gaussian", missing_number=0, regularization=None, mask=None):
         if mu.shape[0] != y.shape[0]:
             raise ValueError("Batch size mismatch between velocity and seismic data")
+        # the reference perturbs x0 only when optimize() ITSELF is passed regularization='diffusion' (core/inversion.py:71);
+        # the constructor's regularization still selects the regulariser when the argument is None (:38-44)
+        noise_x0 = regularization == "diffusion"
         if regularization is None:
             regularization = self.regularization
         reg_fn, builtin = self._resolve_regularizer(regularization)
@@ -114,13 +120,34 @@ class InversionEngine:
         B = mu.shape[0]
         mu = mu.float().clone().detach().to(device).requires_grad_(True)
         mu_true_n = v_normalize(mu_true.float().to(device))                           # core/metrics.py:29
+        multi_rank = getattr(fwi_forward, "world_size", 1) > 1            # sharded operator: collectives stay out of graphs
         y = add_noise_to_seismic(y.to(device), noise_std, noise_type=noise_type)      # core/inversion.py:64-67
         y, trace_mask = missing_trace(y, missing_number, return_mask=True)
         mask = trace_mask if mask is None else mask.to(device) * trace_mask
         y, mask = y.contiguous().float(), mask.contiguous().float()
-        noise_x0 = regularization == "diffusion"                                     # :71-76
+        gen = None
+        if multi_rank:
+            # Every rank holds the replicated model and must see the SAME perturbed data, trace mask, x0 noise and
+            # diffusion timesteps -- each rank's own random stream would make the all-reduced misfit sums and gradients
+            # mix inconsistent data and let the replicated mu drift apart.  Rank 0's draws are broadcast; the per-iteration
+            # randomness comes from a generator every rank seeds with the same (rank-0) seed.
+            import torch.distributed as dist
+            group = getattr(fwi_forward, "group", None)
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            if noise_std > 0 or missing_number > 0:
+                dist.broadcast(y, src=src, group=group)
+                dist.broadcast(mask, src=src, group=group)
+            stochastic = noise_x0 or not builtin
+            if stochastic:
+                if not builtin and not reg_fn.takes_generator:
+                    raise ValueError("a sharded operator needs identical random draws on every rank: a user regulariser that "
+                                     "draws random numbers cannot be synchronised -- use regularization='diffusion' with the "
+                                     "engine's diffusion_model (REDDiffEq takes a generator), or a deterministic regulariser")
+                seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=device)
+                dist.broadcast(seed, src=src, group=group)
+                gen = torch.Generator(device=device)
+                gen.manual_seed(int(seed.item()))
         fused = self.fused_misfit and hasattr(fwi_forward, "misfit")   # any other callable operator: torch loss ops
-        multi_rank = getattr(fwi_forward, "world_size", 1) > 1            # sharded operator: collectives stay out of graphs
         use_graph = (builtin and not multi_rank if self.cuda_graph is None else bool(self.cuda_graph)) and device.type == "cuda"
 
         lr_t = torch.tensor(float(lr), device=device)
@@ -131,13 +158,16 @@ class InversionEngine:
         hist = {k: torch.full((ts, B), float("nan"), device=device) for k in names}
 
         def iteration():
-            x0_pred = mu + self.sigma_x0 * torch.randn_like(mu) if noise_x0 else mu
+            if noise_x0:                                                              # :71-76
+                x0_pred = mu + self.sigma_x0 * torch.randn(mu.shape, device=mu.device, dtype=mu.dtype, generator=gen)
+            else:
+                x0_pred = mu
             if fused:
                 loss_obs = fwi_forward.misfit(x0_pred[:, :, 1:-1, 1:-1], y, mask)
             else:
                 pred = fwi_forward(x0_pred[:, :, 1:-1, 1:-1])                         # :78-79, losses.py:27-36
                 loss_obs = ((y - pred).abs() * mask).sum(dim=(1, 2, 3)) / mask.sum(dim=(1, 2, 3)).clamp(min=1.0)
-            reg_loss = reg_fn(x0_pred)
+            reg_loss = reg_fn(x0_pred, generator=gen) if gen is not None else reg_fn(x0_pred)
             total = loss_obs + reg_lambda * reg_loss                                  # losses.py:54-66
             optimizer.zero_grad(set_to_none=not use_graph)
             total.sum().backward()                                                    # :85-87
@@ -167,7 +197,7 @@ class InversionEngine:
             side = torch.cuda.Stream(device=device)
             side.wait_stream(torch.cuda.current_stream(device))
             with torch.cuda.stream(side):
-                for _ in range(2):
+                for _ in range(min(2, ts)):   # (a third row of a (1, B) history would be out of bounds)
                     iteration()
             torch.cuda.current_stream(device).wait_stream(side)
             torch.cuda.synchronize(device)

@@ -130,11 +130,28 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
 //              sweep runs it; level k of the loop is reverse time t = nt-1-k, the "source" is alpha * cotangent at the
 //              receiver cells, the history receives u_{nt-1} .. u_1 (slot k), and sum_t u_t[src] w_t is accumulated
 //              for the beta_dt term.  The imaging sums are formed afterwards by k_imaging from the two histories.
-// NT = threads per CTA: 512 with one CTA per SM, or 256 with two CTAs (of two different clusters, i.e. two different
-// shots) per SM, so that one can issue while the other sits at its per-level barrier.
-template <int RMAX, int PITCH, bool ADJ, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFwdArgs a, Grid g)
+// One 512-thread CTA per SM (two 256-thread CTAs of two different shots per SM were measured slower and are gone).
+//
+// Debug option "perturb" (ClusterFwdArgs::perturb != 0): pseudo-random per-warp delays in front of every synchronisation
+// point of a level -- halo waits, the sweep with its early halo pushes, the late pushes, the bulk-copy hand-over, the
+// sampling / cotangent warp -- so that the orderings the design relies on (halo write-after-read covered by the data
+// dependency, barriers armed one level ahead, phase parities) are exercised under schedules that never occur in an
+// unperturbed run; results must stay bit-identical (tests/test_gpu_perturb.py).  compute-sanitizer is closed on the pool.
+__device__ __noinline__ void jitter_sleep(const unsigned seed, const unsigned site, const unsigned t)
 {
+    unsigned h = seed ^ (blockIdx.x * 0x9E3779B9u) ^ ((threadIdx.x >> 5) * 0x85EBCA6Bu) ^ (t * 0xC2B2AE35u) ^ (site * 0x27D4EB2Fu);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    if ((h & 3) == 0) __nanosleep((h >> 8) & 0xFFF);  // a quarter of the (warp, level, site) triples sleep up to ~4 us
+}
+__device__ __forceinline__ void jitter(const unsigned seed, const unsigned site, const unsigned t)
+{
+    if (seed != 0) jitter_sleep(seed, site, t);  // cold path kept out of line: the hot loop's register allocation must not change
+}
+
+template <int RMAX, int PITCH, bool ADJ>
+__global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdArgs a, Grid g)
+{
+    constexpr int NT = kClusterThreads;
     extern __shared__ __align__(128) float smem[];
 
     const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
@@ -314,6 +331,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
         auto level = [&](const int t, const int cur, const int prv) {
             const int cbuf = cur == 0 ? 0 : 1, pbuf = 1 - cbuf;
             stamp(t, 0);
+            jitter(a.perturb, 0, (unsigned)t);
             uint64_t *bar_top = bars + 2 * cbuf, *bar_bot = bars + 2 * cbuf + 1;
             const bool sends = t + 1 < a.nt;  // the last level of a shot has no consumer
             // Arm the barriers of the buffer written NOW (consumed at level t+1) before the neighbours' rows can land: a
@@ -332,6 +350,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
                 }
             }
             stamp(t, 1);
+            jitter(a.perturb, 1, (unsigned)t);
             const int p0 = prv + 2 * pitch + th.x;
             const int trev = a.nt - 1 - t;  // adjoint mode: the reverse-time level this iteration computes
             // cotangent pipeline of the last warp: sum the row of the NEXT reverse level (fetched one level ago), then fetch
@@ -345,6 +364,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
                 if (rev) fwd_sweep<RMAX, PITCH, -1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
                 else fwd_sweep<RMAX, PITCH, 1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
                 stamp(t, 2);
+                jitter(a.perturb, 2, (unsigned)t);
                 if (ADJ) {
                     if (th.rec_lr >= 0 && (st1 || trev % a.st == 0)) {  // u_t[rec] += alpha * g_t  (adjoint of the gather, :83)
                         float4 v = ld4(smem + p0 + th.rec_lr * pitch);
@@ -377,6 +397,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
                 }
             }
             stamp(t, 3);
+            jitter(a.perturb, 3, (unsigned)t);
             if (a.hist != nullptr) {
                 fence_proxy_async();             // slab writes -> visible to the bulk-copy engine
                 if (tid == 0) bulk_wait_read();  // the copy of the previous level has finished reading its buffer
@@ -384,6 +405,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
             stamp(t, 4);
             __syncthreads();                     // rows of level t are complete CTA-wide
             stamp(t, 5);
+            jitter(a.perturb, 4, (unsigned)t);
             // Receiver sampling (solvers/pde.py:82-83, after the source injection) is done by the CTA's last warp -- which
             // usually owns no rows -- from the finished level while the other warps already sweep the next one (that
             // buffer is read-only until the barrier after next).  In the owner threads' epilogue it sat on the critical
@@ -416,7 +438,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_fwd_cluster(ClusterFw
 static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, ClusterConfig *cfg)
 {
     const Grid &g = p.g;
-    const int nthreads = p.cluster_threads == 256 ? 256 : kClusterThreads;
+    const int nthreads = kClusterThreads;
     const int groups_max = nthreads / g.q4;
     if (groups_max < 1) return false;
     int max_smem = 0;
@@ -434,8 +456,7 @@ static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, 
         const int slabrows = ngroups * R;  // >= maxrows: rows past the slab are computed but never stored
         size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + g.nxp + 1 + g.nrec + 2 * g.nxp + 2 * g.nrec) * sizeof(float);
         if (smem > (size_t)max_smem) continue;
-        const size_t room = nthreads == 256 ? (size_t)(113 * 1024) : (size_t)max_smem;  // two CTAs per SM must fit 228 KB
-        if (nthreads == 256 && smem > room) continue;
+        const size_t room = (size_t)max_smem;
         cfg->wav_smem = smem + (size_t)p.nt * sizeof(float) <= room;
         if (cfg->wav_smem) smem += (size_t)p.nt * sizeof(float);
         cfg->nthreads = nthreads;
@@ -450,7 +471,7 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots)
 {
     if (p.cluster_rows > 0) return cluster_config_rows(p, p.cluster_rows, true, cfg);  // forced (tests, tuning)
     if (!cluster_config_rows(p, kClusterRowsMax, false, cfg)) return false;
-    if (nshots <= 0 || p.cluster_size != 0 || p.cluster_threads == 256) return true;
+    if (nshots <= 0 || p.cluster_size != 0) return true;
     // Few shots (one model of the reference's configs has 5): the throughput configuration would occupy nshots * C of
     // the 148 SMs and every level would still cost a full 13-row sweep.  A level is latency-bound (one shot's level takes
     // the same time alone as among 33 co-resident ones), so spread a shot over more CTAs with fewer rows per thread --
@@ -465,10 +486,11 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots)
     return true;
 }
 
-template <int R, int PITCH, bool ADJ, int NT>
+template <int R, int PITCH, bool ADJ>
 static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st, int *wave_only)
 {
-    auto kernel = k_fwd_cluster<R, PITCH, ADJ, NT>;
+    constexpr int NT = kClusterThreads;
+    auto kernel = k_fwd_cluster<R, PITCH, ADJ>;
     a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
 
     cudaLaunchConfig_t cfg{};
@@ -513,7 +535,8 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
     }
     const int max_clusters = c_max;
     if (wave_only != nullptr) { *wave_only = max_clusters; return cudaSuccess; }
-    const int ncl = max_clusters < a.nshots ? max_clusters : a.nshots;
+    int ncl = max_clusters < a.nshots ? max_clusters : a.nshots;
+    if (a.max_clusters > 0 && a.max_clusters < ncl) ncl = a.max_clusters;  // the other SMs are busy with the imaging kernel
     cfg.gridDim = dim3((unsigned)(ncl * cc.C));
     e = cudaLaunchKernelEx(&cfg, kernel, a, p.g);
     count_launch();
@@ -527,20 +550,14 @@ static cudaError_t dispatch_fwd_cluster_r(const Plan &p, const ClusterConfig &cc
     // production grids get immediate row offsets (OpenFWI 310+2, Marmousi/Overthrust 430+2); the specialised kernels read
     // x-neighbour PAIRS from shared memory, which needs an even padded width
     switch ((p.g.nxp & 1) == 0 ? p.g.pitch : 0) {
-        case 312: return adj ? launch_fwd_cluster_t<R, 312, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 312, false, 512>(p, cc, a, st, wave_only);
-        case 432: return adj ? launch_fwd_cluster_t<R, 432, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 432, false, 512>(p, cc, a, st, wave_only);
-        default: return adj ? launch_fwd_cluster_t<R, 0, true, 512>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 0, false, 512>(p, cc, a, st, wave_only);
+        case 312: return adj ? launch_fwd_cluster_t<R, 312, true>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 312, false>(p, cc, a, st, wave_only);
+        case 432: return adj ? launch_fwd_cluster_t<R, 432, true>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 432, false>(p, cc, a, st, wave_only);
+        default: return adj ? launch_fwd_cluster_t<R, 0, true>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 0, false>(p, cc, a, st, wave_only);
     }
 }
 
 static cudaError_t dispatch_fwd_cluster(const Plan &p, const ClusterConfig &cc, const ClusterFwdArgs &a, cudaStream_t st, int *wave_only)
 {
-    const bool adj = a.adj_mode != 0;
-    if (cc.nthreads == 256) {  // two CTAs per SM (experimental; OpenFWI pitch and runtime pitch only, 13 rows per thread)
-        if (cc.rmax != kClusterRowsMax) return cudaErrorInvalidValue;
-        if (p.g.pitch == 312 && (p.g.nxp & 1) == 0) return adj ? launch_fwd_cluster_t<kClusterRowsMax, 312, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<kClusterRowsMax, 312, false, 256>(p, cc, a, st, wave_only);
-        return adj ? launch_fwd_cluster_t<kClusterRowsMax, 0, true, 256>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<kClusterRowsMax, 0, false, 256>(p, cc, a, st, wave_only);
-    }
     switch (cc.rmax) {  // rows marched per thread: 13 for throughput, 7 / 4 on wider clusters when the shots are few
         case kClusterRowsMax: return dispatch_fwd_cluster_r<kClusterRowsMax>(p, cc, a, st, wave_only);
         case 7: return dispatch_fwd_cluster_r<7>(p, cc, a, st, wave_only);
@@ -551,6 +568,7 @@ static cudaError_t dispatch_fwd_cluster(const Plan &p, const ClusterConfig &cc, 
 
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
 {
+    a.perturb = (unsigned)p.perturb;
     const_cast<Plan &>(p).last_fwd_C = cc.C;
     const_cast<Plan &>(p).last_fwd_rows = cc.rmax;
     return dispatch_fwd_cluster(p, cc, a, st, nullptr);

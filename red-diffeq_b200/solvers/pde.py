@@ -58,8 +58,10 @@ def _solve_forward(ctx, v_phys, op, need_grad):
     with torch.cuda.device(v.device):
         stream = torch.cuda.current_stream().cuda_stream
         hist, hist_bytes, lease, segment = None, 0, None, 0
+        policy = None
         if need_grad:
-            segment = op._choose_segment(plan, B, v.device)
+            policy = op._choose_segment(plan, B, v.device)
+            segment = policy[0]
             hist_bytes = plan.history_bytes(B, segment)
             lease = op._lease_history(hist_bytes, v.device)
             hist = lease.buffer
@@ -71,6 +73,7 @@ def _solve_forward(ctx, v_phys, op, need_grad):
         op.last_launches = plan.last_launch_count()
     if need_grad:
         ctx.op, ctx.plan, ctx.hist, ctx.hist_bytes, ctx.segment = op, plan, lease, hist_bytes, segment
+        ctx.policy = policy
         ctx.v = v
     return seis, plan, ws, ws_bytes
 
@@ -89,6 +92,9 @@ def _solve_backward(ctx, grad_seis):
     with torch.cuda.device(v.device):
         stream = torch.cuda.current_stream().cuda_stream
         grad_v = torch.empty_like(v)
+        # the plan is shared by every call of the operator: another forward (different batch size) may have moved its
+        # policy-owned options since this graph's forward ran -- put back what that forward decided
+        ctx.op._apply_policy(plan, ctx.policy)
         ws_bytes = plan.workspace_bytes(B)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
         plan.backward(v.data_ptr(), B, g.data_ptr(), grad_v.data_ptr(), ws.data_ptr(), ws_bytes,
@@ -191,6 +197,7 @@ class FWIForward(nn.Module):
     def set_option(self, key, value):
         """Library tunable (see rdfwi_plan_set in include/rdfwi.h); applies to existing and future plans."""
         self.options[key] = int(value)
+        self._segment_auto.clear()   # the history policy was decided under the old options
         for plan in self._plans.values():
             plan.set(key, value)
 
@@ -223,30 +230,42 @@ class FWIForward(nn.Module):
         (memory / (K/2), one extra forward), None = automatic."""
         self._segment = segment
 
+    # options the history policy owns: every decision starts from the user's values (or the library defaults) for these
+    _POLICY_KEYS = ("adj_mode", "u_chunk_shots", "scratch_mb")
+
+    def _apply_policy(self, plan, policy):
+        """Puts the plan into the state a (segment, extras) decision stands for -- as a whole: the policy-owned options
+        that are not part of the decision go back to the user's values, so nothing leaks from an earlier decision
+        (another batch size on the same plan)."""
+        seg, extra = policy
+        for k in self._POLICY_KEYS:
+            plan.set(k, extra.get(k, self.options.get(k, 0)))
+        plan.set("history_segment", seg)
+
     def _choose_segment(self, plan, B, device):
-        """History policy of one forward/backward pair.  Automatic mode walks the tiers until the buffers fit the free
-        HBM: (1) every level + split adjoint (needs a scratch history of the adjoint field); (2) no history at all:
-        the backward pass recomputes the forward field chunk by chunk on the cluster engine (segment = nt, one extra
-        forward, two scratch histories of one or two waves of shots); (3) every level + fused cluster adjoint (no
-        scratch); (4) history checkpointed in time on the per-level engine."""
-        seg = self._segment
+        """History policy of one forward/backward pair: returns (segment, extras) and leaves the plan in that state.
+        Automatic mode walks the tiers until the buffers fit the free HBM: (1) every level + split adjoint (needs a
+        scratch history of the adjoint field); (2) no history at all: the backward pass recomputes the forward field
+        chunk by chunk on the cluster engine (segment = nt, one extra forward, two scratch histories of one or two waves
+        of shots); (3) every level + fused cluster adjoint (no scratch); (4) history checkpointed in time on the
+        per-level engine."""
+        if self._segment is not None:
+            policy = (self._segment, {})
+            self._apply_policy(plan, policy)
+            return policy
         key = (id(plan), B)
-        if seg is None and key in self._segment_auto:   # decided once per (plan, batch): cudaMemGetInfo is slow
-            seg, extra = self._segment_auto[key]
-            for k, v in extra.items():
-                plan.set(k, v)
-        elif seg is None:
+        policy = self._segment_auto.get(key)     # decided once per (plan, batch): cudaMemGetInfo is slow
+        if policy is None:
             free, _total = torch.cuda.mem_get_info(device)
             idle = sum(b.numel() for b in self._history_arena.get(str(device), []))
             budget = 0.9 * (free + idle + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device))
 
-            def fits(segment, **extra):
-                plan.set("history_segment", segment)
-                for k, v in extra.items():
-                    plan.set(k, v)
-                return plan.history_bytes(B, segment) + plan.workspace_bytes(B) <= budget
+            def fits(cand):
+                self._apply_policy(plan, cand)
+                return plan.history_bytes(B, cand[0]) + plan.workspace_bytes(B) <= budget
 
             user = self.options
+            self._apply_policy(plan, (0, {}))
             clustered = user.get("engine", 0) != 1 and plan.get("cluster_size_used") > 0
             wave = plan.get("cluster_wave") if clustered else 0
             tiers = [(0, {})]
@@ -263,7 +282,8 @@ class FWIForward(nn.Module):
             elif "adj_mode" not in user:
                 # per-level engine: the split adjoint streams the adjoint field of a chunk of shots through a scratch
                 # history -- the larger the chunk, the larger (and fewer) its launches: give it the HBM the forward history
-                # leaves free; the fused adjoint needs no scratch history
+                # leaves free; with little room the scratch history shrinks to a few shots (more, smaller chunks) before the
+                # fused adjoint -- which needs no scratch history but moves 32 B per adjoint cell-update -- is considered
                 if "scratch_mb" not in user and "u_chunk_shots" not in user:
                     per_shot = 4.0 * plan.nt * plan.level_floats()
                     spare = 0.9 * (budget - plan.history_bytes(B, 0)) - 4.0 * plan.level_floats() * B * (2 * plan.ns + 4)
@@ -272,16 +292,14 @@ class FWIForward(nn.Module):
                     elif spare >= per_shot:
                         tiers.append((0, {"scratch_mb": int(spare / 1e6)}))
                 tiers.append((0, {"adj_mode": 1}))
-            seg, extra = max(3, int(np.ceil(np.sqrt(2.0 * plan.nt)))), {}   # minimises pairs + segment levels
-            for cand_seg, cand_extra in tiers:
-                if fits(cand_seg, **cand_extra):
-                    seg, extra = cand_seg, cand_extra
+            policy = (max(3, int(np.ceil(np.sqrt(2.0 * plan.nt)))), {})   # minimises pairs + segment levels
+            for cand in tiers:
+                if fits(cand):
+                    policy = cand
                     break
-                for k in cand_extra:   # undo the tier's options before trying the next one
-                    plan.set(k, user.get(k, 0))
-            self._segment_auto[key] = (seg, extra)
-        plan.set("history_segment", seg)
-        return seg
+            self._segment_auto[key] = policy
+        self._apply_policy(plan, policy)
+        return policy
 
     def _lease_history(self, nbytes, device):
         """A history buffer of at least nbytes on `device`, reused across iterations when idle."""

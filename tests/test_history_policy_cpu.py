@@ -17,6 +17,7 @@ class FakePlan:
         self.nt, self.ns, self._level, self.clustered, self.wave = nt, ns, level_floats, clustered, wave
         self.opts = {"history_segment": 0, "adj_mode": 0, "u_chunk_shots": 0, "scratch_mb": 0}
         self.log = []
+        self.size_queries = 0
 
     def level_floats(self):
         return self._level
@@ -41,6 +42,7 @@ class FakePlan:
         return per_level * 2 * (math.ceil(self.nt / segment) - 1)
 
     def workspace_bytes(self, B):
+        self.size_queries += 1
         o, per_shot = self.opts, 4.0 * self.nt * self._level
         shots = B * self.ns
         small = 4.0 * self._level * B * (2 * self.ns + 4)
@@ -68,29 +70,31 @@ def _op(monkeypatch, free_gb):
 
 def test_everything_fits_keeps_every_level(monkeypatch):
     op, plan = _op(monkeypatch, 178), FakePlan()
-    assert op._choose_segment(plan, 64, torch.device("cuda:0")) == 0       # 123.8 GB history + 24.8 GB scratch + planes
+    assert op._choose_segment(plan, 64, torch.device("cuda:0")) == (0, {})  # 123.8 GB history + 24.8 GB scratch + planes
     assert plan.opts["adj_mode"] == 0 and plan.opts["u_chunk_shots"] == 0
-    n = len(plan.log)
-    assert op._choose_segment(plan, 64, torch.device("cuda:0")) == 0       # cached: no new size queries, only the option set
-    assert len(plan.log) == n + 1 and plan.log[-1] == ("history_segment", 0)
+    n = plan.size_queries
+    assert op._choose_segment(plan, 64, torch.device("cuda:0")) == (0, {})  # cached: no new size queries, only the options set
+    assert plan.size_queries == n and plan.log[-1] == ("history_segment", 0)
+    op.set_option("img_prefetch", 8)                                        # any option change invalidates the cached decisions
+    assert op._segment_auto == {}
 
 
 def test_batch_too_large_for_a_history_recomputes_the_forward_field(monkeypatch):
     op, plan = _op(monkeypatch, 178), FakePlan()
-    seg = op._choose_segment(plan, 96, torch.device("cuda:0"))             # 185.7 GB of history: does not fit
+    seg, _ = op._choose_segment(plan, 96, torch.device("cuda:0"))          # 185.7 GB of history: does not fit
     assert seg == plan.nt and plan.history_bytes(96, seg) == 0 and plan.opts["history_segment"] == plan.nt
 
 
 def test_long_record_prefers_recomputing_over_the_fused_adjoint(monkeypatch):
     op = _op(monkeypatch, 178)
     plan = FakePlan(nt=16000, level_floats=310 * 432, wave=22)             # 8.6 GB per shot: < a wave of shots per 40 GB
-    seg = op._choose_segment(plan, 8, torch.device("cuda:0"))
+    seg, _ = op._choose_segment(plan, 8, torch.device("cuda:0"))
     assert seg == plan.nt and plan.opts["adj_mode"] == 0
 
 
 def test_little_memory_falls_back_to_checkpoints_in_time(monkeypatch):
     op, plan = _op(monkeypatch, 12), FakePlan()
-    seg = op._choose_segment(plan, 64, torch.device("cuda:0"))
+    seg, _ = op._choose_segment(plan, 64, torch.device("cuda:0"))
     assert seg == math.ceil(math.sqrt(2.0 * plan.nt)) and 0 < plan.history_bytes(64, seg) < 12 * GB
     assert plan.opts["adj_mode"] == 0 and plan.opts["u_chunk_shots"] == 0   # the rejected tiers' options were undone
 
@@ -98,13 +102,28 @@ def test_little_memory_falls_back_to_checkpoints_in_time(monkeypatch):
 def test_per_level_engine_sizes_its_scratch_history_from_the_free_memory(monkeypatch):
     op = _op(monkeypatch, 178)
     plan = FakePlan(ns=16, level_floats=1264 * 1264, clustered=False)      # interior 1024^2: 6.4 GB per shot
-    assert op._choose_segment(plan, 1, torch.device("cuda:0")) == 0
+    assert op._choose_segment(plan, 1, torch.device("cuda:0"))[0] == 0
     assert plan.opts["scratch_mb"] > 40000                                  # more than the default cap: larger, fewer launches
     tight = FakePlan(ns=24, level_floats=1264 * 1264, clustered=False)     # 153 GB of history: no room for a scratch history
-    assert op._choose_segment(tight, 1, torch.device("cuda:0")) == 0 and tight.opts["adj_mode"] == 1
+    assert op._choose_segment(tight, 1, torch.device("cuda:0"))[0] == 0 and tight.opts["adj_mode"] == 1
 
 
 def test_explicit_segment_is_respected(monkeypatch):
     op, plan = _op(monkeypatch, 178), FakePlan()
     op.set_history_segment(16)
-    assert op._choose_segment(plan, 4, torch.device("cuda:0")) == 16 and plan.log == [("history_segment", 16)]
+    assert op._choose_segment(plan, 4, torch.device("cuda:0")) == (16, {}) and plan.log[-1] == ("history_segment", 16)
+    assert plan.opts["adj_mode"] == 0 and plan.opts["u_chunk_shots"] == 0 and plan.opts["scratch_mb"] == 0
+
+
+def test_decisions_for_different_batches_do_not_leak_into_each_other(monkeypatch):
+    """forward(B1), forward(B2), backward(B1) on one plan: every decision is applied as a whole, and the backward pass
+    re-applies the decision its own forward took (the options of the last decision used to stay set)."""
+    op = _op(monkeypatch, 178)
+    plan = FakePlan(ns=24, level_floats=1264 * 1264, clustered=False)
+    tight = op._choose_segment(plan, 1, torch.device("cuda:0"))            # no room for a scratch history: fused adjoint
+    assert tight == (0, {"adj_mode": 1}) and plan.opts["adj_mode"] == 1
+    plan.ns = 4                                                            # "another batch": plenty of room
+    roomy = op._choose_segment(plan, 2, torch.device("cuda:0"))
+    assert roomy[0] == 0 and plan.opts["adj_mode"] == 0 and plan.opts["scratch_mb"] > 40000
+    op._apply_policy(plan, tight)                                          # what _solve_backward does for the first graph
+    assert plan.opts["adj_mode"] == 1 and plan.opts["scratch_mb"] == 0 and plan.opts["history_segment"] == 0

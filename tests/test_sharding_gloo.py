@@ -176,3 +176,48 @@ def test_inversion_engine_on_a_sharded_operator(tmp_path, oracle):
     assert np.allclose(r0["obs"], obs_single, rtol=5e-4)          # Adam amplifies the different summation order a little
     assert np.allclose(r0["mu"], mu_single, atol=2e-3)
     assert (obs_single[:, -1] < obs_single[:, 0]).all()
+
+
+def _stochastic_engine_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(1000 + 17 * rank)                   # every rank's own stream differs, as in a real launch
+    from red_diffeq_b200 import InversionEngine
+    from red_diffeq_b200.solvers.sharding import ShardedFWIForward
+    from toy_models import TinyDiffusion
+    rng = np.random.default_rng(9)
+    B = 2
+    mu_true_n = (0.6 * rng.random((B, 1, NZ, NX)) - 0.3).astype(np.float32)
+    op = ShardedFWIForward(dict(CTX), "cpu", mode="shots",
+                           operator_factory=lambda ctx, dev, shot_subset=None: _OracleOp(ctx, dev, shot_subset, normalize=True))
+    with torch.no_grad():
+        y = _OracleOp(dict(CTX), "cpu", None, normalize=True)(torch.tensor(mu_true_n))
+    mu0 = torch.nn.functional.pad(torch.zeros(B, 1, NZ, NX), (1, 1, 1, 1))
+    mu_true = (torch.tensor(mu_true_n) + 1) / 2 * 3000 + 1500
+    eng = InversionEngine(TinyDiffusion(), regularization="diffusion", sigma_x0=1e-2)
+    eng.device = torch.device("cpu")
+    mu, res = eng.optimize(mu0, mu_true, y, op, ts=3, lr=0.03, reg_lambda=0.05, noise_std=1e-4, missing_number=3,
+                           regularization="diffusion")
+    out = {"mu": mu.detach().numpy(), "obs": np.array([r["obs_losses"] for r in res]), "reg": np.array([r["reg_losses"] for r in res])}
+    # a user regulariser that cannot be handed a generator is refused on a sharded operator
+    try:
+        InversionEngine(regularizer=lambda m: torch.rand(m.shape[0]), regularization="tv").optimize(
+            mu0, mu_true, y, op, ts=1, regularization="tv")
+        out["refused"] = np.array(0)
+    except ValueError:
+        out["refused"] = np.array(1)
+    np.savez(os.path.join(out_dir, f"stoch{rank}.npz"), **out)
+    dist.destroy_process_group()
+
+
+def test_sharded_engine_draws_the_same_random_numbers_on_every_rank(tmp_path, oracle):
+    """with noise, missing traces, x0 noise and the diffusion regulariser's timesteps every rank must see
+    rank 0's draws -- otherwise the all-reduced sums mix inconsistent data and the replicated mu drifts apart."""
+    port = 35500 + os.getpid() % 2000
+    mp.spawn(_stochastic_engine_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "stoch0.npz"), np.load(tmp_path / "stoch1.npz")
+    assert np.array_equal(r0["mu"], r1["mu"])
+    assert np.array_equal(r0["obs"], r1["obs"]) and np.array_equal(r0["reg"], r1["reg"])
+    assert np.abs(r0["reg"]).max() > 0 and int(r0["refused"]) == 1 and int(r1["refused"]) == 1
