@@ -473,7 +473,7 @@ def measure_workload(env, workload, steps, warmup, opts=(), history_segment=None
         "h2d": int(vn_host.numel() * 4 + y_host.numel() * 4), "d2h": int(grad_host.numel() * 4 + loss_host.numel() * 4),
         "options": dict(op.options), "segment": seg,
         "plan": {k: plan.get(k) for k in ("adj_split", "cluster_size_used", "adj_cluster_size_used", "cluster_size_last",
-                                           "cluster_rows_last", "u_chunk_used", "adj_overlap_used", "cluster_wave")},
+                                           "cluster_rows_last", "u_chunk_used", "cluster_wave")},
         "engine_opt": op.options.get("engine", 0),
         "resident_gb": (plan.history_bytes(B, seg) + plan.workspace_bytes(B)) / 1e9,
     }
@@ -561,7 +561,6 @@ def roofline_block(m, steps):
         "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algo_bytes"] / max(dom["launches"], 1),
         "avg_launch_us": dom["avg_launch_us"], "launches_per_step": dom["launches"],
         "share_of_step": dom["us"] * 1e-3 / ms_per_step,
-        "overlapped_adjoint": bool(p["adj_overlap_used"]),
         "kernels": {k: {"kernel": v["kernel"], "ms_per_step": v["us"] * 1e-3, "launches_per_step": v["launches"],
                         "algorithmic_GB_per_step": v["algo_bytes"] / 1e9, "achieved_gbs": v["achieved_gbs"], "frac": v["frac"],
                         "traffic": v["traffic"], "ncu_dram_gbs_from_profile": v["ncu_gbs"],
@@ -588,8 +587,6 @@ def config_block(m):
     if adj_split:
         adj_txt = ("split: per-level tiled adjoint field + streaming imaging" if p["adj_split"] == 3 else
                    "split: cluster-resident adjoint field (C=%d) + streaming imaging" % p["cluster_size_last"])
-        if p["adj_overlap_used"]:
-            adj_txt += (", overlapped: adjoint field of chunk k+1 on %d clusters beside the imaging kernel of chunk k" % p["adj_overlap_used"])
     return {"workload": m["workload"], "models_per_gpu": m["B"], "shots_per_model": m["ns"], "shots_on_rank0": m["ns_local"],
             "nt": m["nt"], "padded_grid": [m["nzp"], m["nxp"]], "pairs_per_step_per_gpu": m["pairs_rank"],
             "l2_policy": "working set (wavefield histories, %.1f GB streamed per step) far exceeds the 126 MB L2; no flush needed" % m["resident_gb"],
@@ -762,9 +759,10 @@ def red_iter_block(env, args):
             reg_ms_ours = time_reg(lambda mu: ours(mu))
             solver_ms = time_solver()
             s_ref, _ = time_loop(InversionEngine(regularization="diffusion", regularizer=lambda mu: ref_method.get_reg_loss(mu), cuda_graph=False))
-            s_ours, res = time_loop(InversionEngine(dm, regularization="diffusion", cuda_graph=False))
+            s_serial, _ = time_loop(InversionEngine(dm, regularization="diffusion", cuda_graph=False, overlap_regularizer=False))
+            s_ours, res = time_loop(InversionEngine(dm, regularization="diffusion", cuda_graph=False))   # U-Net beside the forward kernel
             blk = {"models": B, "shots": ctx["ns"], "nt": ctx["nt"], "iterations_timed": ts,
-                   "s_per_iter": s_ours, "s_per_iter_reference_pattern": s_ref,
+                   "s_per_iter": s_ours, "s_per_iter_regulariser_not_overlapped": s_serial, "s_per_iter_reference_pattern": s_ref,
                    "solver_ms": solver_ms, "solver_share": solver_ms * 1e-3 / s_ours,
                    "reg_ms_reference_pattern": reg_ms_ref, "reg_ms_ours": reg_ms_ours,
                    "pairs_per_s_through_the_iteration": pairs / s_ours,

@@ -77,7 +77,13 @@ int rdfwi_plan_destroy(rdfwi_plan plan);
  *   "rows_per_thread" (1, 2, 4, 8; tile rows = 8x) / "adj_rows_per_thread"  z-rows marched per thread, per-level kernels
  *   "chunk_models"   models advanced together by the per-level forward (0 = auto)
  *   "timing"         1 = record CUDA events around each kernel class on the caller's stream (read back as "us_<class>",
- *                    "n_<class>" with class in forward, adjoint_field, imaging, adjoint_loop)
+ *                    "n_<class>" with class in forward, adjoint_field, imaging, adjoint_loop).  EXCEPTION to "the library
+ *                    never synchronises": rdfwi_plan_get("us_*" / "n_*") waits (cudaEventSynchronize) for the recorded
+ *                    events, i.e. for the timed work -- a measurement hook, never called by forward / backward themselves
+ *   "perturb"        debug: seed (> 0) of pseudo-random per-warp delays (up to ~4 us) in front of every synchronisation point
+ *                    of the cluster-resident time loop -- halo waits, early / late halo pushes, bulk-copy hand-over, sampling
+ *                    warp -- run by separate kernel instantiations; results must not change (tests/test_gpu_perturb.py: the
+ *                    substitute for racecheck, which is closed on the GPU pool).  0 = off (production kernels)
  * rdfwi_plan_get additionally answers "pitch", "nzp", "nxp", "nt_out", "cluster_size_used", "adj_cluster_size_used", "cluster_size_last", "cluster_rows_last" (what the
  * last cluster-resident launch ran),
  * "cluster_wave" (co-resident clusters of the forward configuration), "adj_split" (what the last backward ran: 0 fused,

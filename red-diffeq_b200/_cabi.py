@@ -12,7 +12,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
-LIB_PATH = os.path.join(_PKG, "librdfwi.so")
+LIB_PATH = os.environ.get("RDFWI_LIB") or os.path.join(_PKG, "librdfwi.so")   # RDFWI_LIB: A/B builds of the same sources
 SOURCES = ["rdfwi_api.cu", "kernels_prologue.cu", "kernels_step.cu", "kernels_tile.cu", "kernels_cluster.cu", "kernels_cluster_adj.cu", "kernels_imaging.cu", "kernels_epilogue.cu", "kernels_misfit.cu"]
 HEADERS = [os.path.join(_CSRC, "rdfwi_common.cuh"), os.path.join(_CSRC, "cluster_ptx.cuh"), os.path.join(_ROOT, "include", "rdfwi.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
@@ -35,18 +35,20 @@ def _nvcc():
     return "nvcc"
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu into librdfwi.so for sm_100a (nvcc cross-compiles without a GPU)."""
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile csrc/*.cu into librdfwi.so for sm_100a (nvcc cross-compiles without a GPU).  `defines` / `out`: an A/B
+    variant of the same sources under another file name (loaded with RDFWI_LIB=<path>)."""
     srcs = [os.path.join(_CSRC, s) for s in SOURCES]
     deps = srcs + HEADERS
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
-        return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH] + srcs
+    out = out or LIB_PATH
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-I", os.path.join(_ROOT, "include"), "-o", out] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     subprocess.check_call(cmd)
-    return LIB_PATH
+    return out
 
 
 class _Survey(ctypes.Structure):

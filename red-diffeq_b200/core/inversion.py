@@ -51,10 +51,22 @@ class InversionEngine:
     ssim_loss:      optional callable (pred01, true01) -> scalar, evaluated per model like core/metrics.py:41-44
                     (None: the 'ssim' history is NaN -- the SSIM module is not part of the hot path).
     fused_misfit:   use fwi_forward.misfit (default) or the operator + torch loss ops.
-    cuda_graph:     None = automatic (on for the built-in regularisers, off for a user callable), True / False."""
+    cuda_graph:     None = automatic (on for the built-in regularisers and for the diffusion regulariser built from
+                    `diffusion_model`; off for a user callable and on a sharded operator), True / False.  A graphed run
+                    draws its x0 noise / timesteps from the same seeded generator but at other Philox offsets than an eager
+                    run (the two warm-up iterations draw too): seeded runs reproduce themselves, not the eager stream --
+                    pass cuda_graph=False to draw exactly what the reference's loop draws.
+    overlap_regularizer: evaluate the regulariser on a second CUDA stream while the operator's forward kernel runs
+                    (SURVEY.md 5 / 8e "overlap with the U-Net regulariser"): the two depend only on x0.  One model of the
+                    reference's configs leaves 68 of 148 SMs idle during the solve -- room for the U-Net's kernels.  Pays
+                    only inside a CUDA graph (eager, the one Python thread issues the ~600 U-Net launches back to back and
+                    the solver's launches queue behind them: measured 12.7 vs 12.2 ms per Marmousi iteration eager, 8.7 vs
+                    10.7 ms graphed).  None = automatic (on when the iteration is graphed and the regulariser is the
+                    diffusion one), True / False."""
 
     def __init__(self, diffusion_model=None, ssim_loss=None, regularization=None, use_time_weight=False,
-                 sigma_x0=0.0001, fixed_timestep=None, *, regularizer=None, fused_misfit=True, cuda_graph=None):
+                 sigma_x0=0.0001, fixed_timestep=None, *, regularizer=None, fused_misfit=True, cuda_graph=None,
+                 overlap_regularizer=None):
         self.diffusion_model = diffusion_model
         self.ssim_loss = ssim_loss
         self.regularization = regularization
@@ -67,6 +79,7 @@ class InversionEngine:
         self.sigma_x0 = sigma_x0
         self.fused_misfit = fused_misfit
         self.cuda_graph = cuda_graph
+        self.overlap_regularizer = overlap_regularizer
         self.used_cuda_graph = False
         self.last_loop_seconds = None
         self.device = getattr(diffusion_model, "device", None)
@@ -148,7 +161,11 @@ class InversionEngine:
                 gen = torch.Generator(device=device)
                 gen.manual_seed(int(seed.item()))
         fused = self.fused_misfit and hasattr(fwi_forward, "misfit")   # any other callable operator: torch loss ops
-        use_graph = (builtin and not multi_rank if self.cuda_graph is None else bool(self.cuda_graph)) and device.type == "cuda"
+        graphable = builtin or reg_fn.takes_generator     # stock regularisers and REDDiffEq (denoiser under no_grad)
+        use_graph = (graphable and not multi_rank if self.cuda_graph is None else bool(self.cuda_graph)) and device.type == "cuda"
+
+        overlap_reg = ((reg_fn.takes_generator and use_graph) if self.overlap_regularizer is None else bool(self.overlap_regularizer)) and device.type == "cuda"
+        reg_stream = torch.cuda.Stream(device=device) if overlap_reg else None
 
         lr_t = torch.tensor(float(lr), device=device)
         step_t = torch.zeros(1, dtype=torch.long, device=device)
@@ -162,12 +179,22 @@ class InversionEngine:
                 x0_pred = mu + self.sigma_x0 * torch.randn(mu.shape, device=mu.device, dtype=mu.dtype, generator=gen)
             else:
                 x0_pred = mu
+            if overlap_reg:   # the regulariser needs x0 only: it runs beside the operator's forward kernel (its backward is
+                cur = torch.cuda.current_stream(device)      # run by autograd on the same side stream and joined there)
+                reg_stream.wait_stream(cur)
+                x0_pred.record_stream(reg_stream)
+                with torch.cuda.stream(reg_stream):
+                    reg_loss = reg_fn(x0_pred, generator=gen) if gen is not None else reg_fn(x0_pred)
             if fused:
                 loss_obs = fwi_forward.misfit(x0_pred[:, :, 1:-1, 1:-1], y, mask)
             else:
                 pred = fwi_forward(x0_pred[:, :, 1:-1, 1:-1])                         # :78-79, losses.py:27-36
                 loss_obs = ((y - pred).abs() * mask).sum(dim=(1, 2, 3)) / mask.sum(dim=(1, 2, 3)).clamp(min=1.0)
-            reg_loss = reg_fn(x0_pred, generator=gen) if gen is not None else reg_fn(x0_pred)
+            if overlap_reg:
+                cur.wait_stream(reg_stream)
+                reg_loss.record_stream(cur)
+            else:
+                reg_loss = reg_fn(x0_pred, generator=gen) if gen is not None else reg_fn(x0_pred)
             total = loss_obs + reg_lambda * reg_loss                                  # losses.py:54-66
             optimizer.zero_grad(set_to_none=not use_graph)
             total.sum().backward()                                                    # :85-87

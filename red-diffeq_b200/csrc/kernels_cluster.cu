@@ -143,12 +143,15 @@ __device__ __noinline__ void jitter_sleep(const unsigned seed, const unsigned si
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
     if ((h & 3) == 0) __nanosleep((h >> 8) & 0xFFF);  // a quarter of the (warp, level, site) triples sleep up to ~4 us
 }
+// PERT is a template parameter: even five out-of-line calls behind a uniform `seed != 0` branch per level cost the
+// production kernels 3 ms of 38 (measured, profiles/README.md round 2), so they are compiled without any trace of it.
+template <bool PERT>
 __device__ __forceinline__ void jitter(const unsigned seed, const unsigned site, const unsigned t)
 {
-    if (seed != 0) jitter_sleep(seed, site, t);  // cold path kept out of line: the hot loop's register allocation must not change
+    if (PERT) jitter_sleep(seed, site, t);
 }
 
-template <int RMAX, int PITCH, bool ADJ>
+template <int RMAX, int PITCH, bool ADJ, bool PERT>
 __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdArgs a, Grid g)
 {
     constexpr int NT = kClusterThreads;
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
         auto level = [&](const int t, const int cur, const int prv) {
             const int cbuf = cur == 0 ? 0 : 1, pbuf = 1 - cbuf;
             stamp(t, 0);
-            jitter(a.perturb, 0, (unsigned)t);
+            jitter<PERT>(a.perturb, 0, (unsigned)t);
             uint64_t *bar_top = bars + 2 * cbuf, *bar_bot = bars + 2 * cbuf + 1;
             const bool sends = t + 1 < a.nt;  // the last level of a shot has no consumer
             // Arm the barriers of the buffer written NOW (consumed at level t+1) before the neighbours' rows can land: a
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                 }
             }
             stamp(t, 1);
-            jitter(a.perturb, 1, (unsigned)t);
+            jitter<PERT>(a.perturb, 1, (unsigned)t);
             const int p0 = prv + 2 * pitch + th.x;
             const int trev = a.nt - 1 - t;  // adjoint mode: the reverse-time level this iteration computes
             // cotangent pipeline of the last warp: sum the row of the NEXT reverse level (fetched one level ago), then fetch
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                 if (rev) fwd_sweep<RMAX, PITCH, -1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
                 else fwd_sweep<RMAX, PITCH, 1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
                 stamp(t, 2);
-                jitter(a.perturb, 2, (unsigned)t);
+                jitter<PERT>(a.perturb, 2, (unsigned)t);
                 if (ADJ) {
                     if (th.rec_lr >= 0 && (st1 || trev % a.st == 0)) {  // u_t[rec] += alpha * g_t  (adjoint of the gather, :83)
                         float4 v = ld4(smem + p0 + th.rec_lr * pitch);
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                 }
             }
             stamp(t, 3);
-            jitter(a.perturb, 3, (unsigned)t);
+            jitter<PERT>(a.perturb, 3, (unsigned)t);
             if (a.hist != nullptr) {
                 fence_proxy_async();             // slab writes -> visible to the bulk-copy engine
                 if (tid == 0) bulk_wait_read();  // the copy of the previous level has finished reading its buffer
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
             stamp(t, 4);
             __syncthreads();                     // rows of level t are complete CTA-wide
             stamp(t, 5);
-            jitter(a.perturb, 4, (unsigned)t);
+            jitter<PERT>(a.perturb, 4, (unsigned)t);
             // Receiver sampling (solvers/pde.py:82-83, after the source injection) is done by the CTA's last warp -- which
             // usually owns no rows -- from the finished level while the other warps already sweep the next one (that
             // buffer is read-only until the barrier after next).  In the owner threads' epilogue it sat on the critical
@@ -486,11 +489,11 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots)
     return true;
 }
 
-template <int R, int PITCH, bool ADJ>
+template <int R, int PITCH, bool ADJ, bool PERT>
 static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st, int *wave_only)
 {
     constexpr int NT = kClusterThreads;
-    auto kernel = k_fwd_cluster<R, PITCH, ADJ>;
+    auto kernel = k_fwd_cluster<R, PITCH, ADJ, PERT>;
     a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
 
     cudaLaunchConfig_t cfg{};
@@ -535,24 +538,31 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
     }
     const int max_clusters = c_max;
     if (wave_only != nullptr) { *wave_only = max_clusters; return cudaSuccess; }
-    int ncl = max_clusters < a.nshots ? max_clusters : a.nshots;
-    if (a.max_clusters > 0 && a.max_clusters < ncl) ncl = a.max_clusters;  // the other SMs are busy with the imaging kernel
+    const int ncl = max_clusters < a.nshots ? max_clusters : a.nshots;
     cfg.gridDim = dim3((unsigned)(ncl * cc.C));
     e = cudaLaunchKernelEx(&cfg, kernel, a, p.g);
     count_launch();
     return e;
 }
 
+template <int R, int PITCH>
+static cudaError_t dispatch_fwd_cluster_rp(const Plan &p, const ClusterConfig &cc, const ClusterFwdArgs &a, cudaStream_t st, int *wave_only)
+{
+    const bool adj = a.adj_mode != 0;
+    if (a.perturb != 0)  // debug instantiations (schedule perturbation)
+        return adj ? launch_fwd_cluster_t<R, PITCH, true, true>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, PITCH, false, true>(p, cc, a, st, wave_only);
+    return adj ? launch_fwd_cluster_t<R, PITCH, true, false>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, PITCH, false, false>(p, cc, a, st, wave_only);
+}
+
 template <int R>
 static cudaError_t dispatch_fwd_cluster_r(const Plan &p, const ClusterConfig &cc, const ClusterFwdArgs &a, cudaStream_t st, int *wave_only)
 {
-    const bool adj = a.adj_mode != 0;
     // production grids get immediate row offsets (OpenFWI 310+2, Marmousi/Overthrust 430+2); the specialised kernels read
     // x-neighbour PAIRS from shared memory, which needs an even padded width
     switch ((p.g.nxp & 1) == 0 ? p.g.pitch : 0) {
-        case 312: return adj ? launch_fwd_cluster_t<R, 312, true>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 312, false>(p, cc, a, st, wave_only);
-        case 432: return adj ? launch_fwd_cluster_t<R, 432, true>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 432, false>(p, cc, a, st, wave_only);
-        default: return adj ? launch_fwd_cluster_t<R, 0, true>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, 0, false>(p, cc, a, st, wave_only);
+        case 312: return dispatch_fwd_cluster_rp<R, 312>(p, cc, a, st, wave_only);
+        case 432: return dispatch_fwd_cluster_rp<R, 432>(p, cc, a, st, wave_only);
+        default: return dispatch_fwd_cluster_rp<R, 0>(p, cc, a, st, wave_only);
     }
 }
 

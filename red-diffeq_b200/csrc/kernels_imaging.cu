@@ -15,8 +15,6 @@
 // halos, the two sums and u_{m+1}, u_{m+2} in registers for the whole time loop.  (Checked against the stencil form
 // in fp64: identical to 4e-15; in fp32 both forms are equally far from the fp64 result, 1.9e-5 on the OpenFWI case.)
 // This is the HBM-bound part of the adjoint.
-#include <algorithm>
-
 #include "rdfwi_common.cuh"
 
 namespace rdfwi {
@@ -36,21 +34,16 @@ __device__ __forceinline__ int sponge_index(int i, int n, int nbc)
     return i < nbc ? nbc - 1 - i : (i >= n - nbc ? i - (n - nbc) : -1);
 }
 
-// A work item = 256 float4 slots of one shot; a thread owns one float4 of one shot for all levels.  The grid is 1-D:
-// one CTA per work item, or -- when the launch has to stay on the SMs the next chunk's adjoint-field kernel leaves
-// free -- a persistent grid that strides over the work items.
+// grid = (float4 slots of a level / 256, shots of the chunk); a thread owns one float4 of one shot for all levels
 __global__ void __launch_bounds__(kImgThreads) k_imaging(const float *__restrict__ phist, const float *__restrict__ uhist,
                                                          const float *__restrict__ alpha, const float *__restrict__ kap,
                                                          const float *__restrict__ beta_src, const float *__restrict__ Gb,
                                                          const int *__restrict__ isx, float *__restrict__ Ga,
-                                                         float *__restrict__ Gk, Grid g, int nt, int shot0, int pshot0, int prefetch,
-                                                         int tiles, int nitems)
+                                                         float *__restrict__ Gk, Grid g, int nt, int shot0, int pshot0, int prefetch)
 {
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int shot_l = item / tiles;
-    const int i = (item - shot_l * tiles) * kImgThreads + threadIdx.x;  // float4 slot
-    if (i >= g.nzp * g.q4) continue;
-    const int shot = shot0 + shot_l, b = shot / g.ns;
+    const int i = blockIdx.x * kImgThreads + threadIdx.x;  // float4 slot
+    if (i >= g.nzp * g.q4) return;
+    const int shot_l = blockIdx.y, shot = shot0 + shot_l, b = shot / g.ns;
     const int z = i / g.q4, x = (i - z * g.q4) * 4;
     const size_t cell = (size_t)i * 4;
     const size_t lvl = g.level;
@@ -108,7 +101,6 @@ __global__ void __launch_bounds__(kImgThreads) k_imaging(const float *__restrict
     const size_t off = (size_t)shot * lvl + cell;
     *reinterpret_cast<float4 *>(Ga + off) = make_float4(ga[0] / (a4[0] * a4[0]), ga[1] / (a4[1] * a4[1]), ga[2] / (a4[2] * a4[2]), ga[3] / (a4[3] * a4[3]));
     *reinterpret_cast<float4 *>(Gk + off) = make_float4(gk[0] / a4[0], gk[1] / a4[1], gk[2] / a4[2], gk[3] / a4[3]);
-  }
 }
 
 }  // namespace
@@ -117,25 +109,13 @@ __global__ void __launch_bounds__(kImgThreads) k_imaging(const float *__restrict
 // history recomputed in the backward pass)
 cudaError_t launch_imaging(const Plan &p, const float *phist, const float *uhist, const float *alpha, const float *kap,
                            const float *beta_src, const float *Gb, float *Ga, float *Gk, int shot0, int nshots, int pshot0,
-                           int max_sms, cudaStream_t st)
+                           cudaStream_t st)
 {
     const Grid &g = p.g;
     const int slots = g.nzp * g.q4;
-    const int tiles = (slots + kImgThreads - 1) / kImgThreads;
-    const long long nitems = (long long)tiles * nshots;
-    if (nitems > 0x7fffffffLL) return cudaErrorInvalidValue;
-    long long grid = nitems;
-    if (max_sms > 0) {
-        if (p.img_occ == 0) {
-            int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_imaging, kImgThreads, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
-            p.img_occ = occ;
-        }
-        grid = std::min(nitems, (long long)max_sms * p.img_occ);
-    }
+    const dim3 grid((slots + kImgThreads - 1) / kImgThreads, nshots);
     const int pf = p.img_prefetch > 0 ? p.img_prefetch : 4;
-    k_imaging<<<(unsigned)grid, kImgThreads, 0, st>>>(phist, uhist, alpha, kap, beta_src, Gb, p.d_isx, Ga, Gk, g, p.nt, shot0, pshot0, pf,
-                                                     tiles, (int)nitems);
+    k_imaging<<<grid, kImgThreads, 0, st>>>(phist, uhist, alpha, kap, beta_src, Gb, p.d_isx, Ga, Gk, g, p.nt, shot0, pshot0, pf);
     count_launch();
     return cudaGetLastError();
 }

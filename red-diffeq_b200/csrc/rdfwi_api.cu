@@ -117,20 +117,7 @@ struct Workspace {
     int u_chunk = 0;
     float *u_hist = nullptr;
     float *p_hist = nullptr;  // recompute mode: forward history of one chunk of shots
-    int ov_clusters = 0;      // > 0: overlapped split adjoint -- the adjoint-field kernel of chunk k+1 runs on this many clusters
-                              // while the imaging kernel of chunk k streams on the other SMs; scratch histories are double-buffered
-    float *u_hist2 = nullptr, *p_hist2 = nullptr;
 };
-
-// Clusters the adjoint-field kernel keeps when it shares the device with the imaging kernel of the previous chunk.
-// The two kernels are complementary: the cluster kernel is bound on chip (shared-memory pipe, latency) and uses half of
-// the HBM bandwidth, the imaging kernel is a pure HBM stream that needs few SMs' worth of issue slots.
-int overlap_clusters(const Plan &p, int wave, int nshots)
-{
-    if (p.adj_overlap < 0 || wave < 4) return 0;
-    if (p.adj_overlap > 0) return std::min(p.adj_overlap, wave);
-    return 0;  // auto rule filled in from measurements (profiles/overlap_r2.md)
-}
 
 int cached_wave(const Plan &p, const ClusterConfig &cc) { return fwd_cluster_wave(p, cc); }  // cached per configuration
 
@@ -175,23 +162,14 @@ Workspace carve(const Plan &p, int B, void *base)
         // cap on one scratch history: 40 GB beside a full forward history, 55 GB each for the two of the recompute tier
         const double cap = p.scratch_mb > 0 ? 1e6 * (double)p.scratch_mb : (single_segment ? 55e9 : 40e9);
         int chunk = p.u_chunk_shots;
-        int ov = overlap_clusters(p, wave, nshots);
         if (chunk <= 0) {
             const int fit = std::max(1, (int)(cap / per_shot));
             chunk = fit >= 2 * wave ? 2 * wave : (fit >= wave ? wave : fit);
-            // overlapped: two scratch histories in flight (same total cap), each two rounds of the reduced cluster count
-            if (ov > 0) {
-                const int fit2 = std::max(1, (int)(0.5 * cap / per_shot));
-                if (fit2 >= ov && nshots > 2 * ov) chunk = fit2 >= 2 * ov ? 2 * ov : ov;
-                else ov = 0;
-            }
         }
         chunk = std::min(chunk, nshots);
         const int nchunks = (nshots + chunk - 1) / chunk;
         w.u_chunk = (nshots + nchunks - 1) / nchunks;
-        if (nchunks < 2) ov = 0;  // nothing to pipeline
-        w.ov_clusters = ov;
-        if (p.u_chunk_shots == 0 && !single_segment && w.u_chunk < nshots && w.u_chunk < wave && ov == 0 && fused_ok) { w.split = false; w.u_chunk = 0; w.ov_clusters = 0; }
+        if (p.u_chunk_shots == 0 && !single_segment && w.u_chunk < nshots && w.u_chunk < wave && fused_ok) { w.split = false; w.u_chunk = 0; }
     }
     w.fused = fused_ok && !w.split;
     // per-level engine, every level kept: the adjoint is split too (tiled adjoint-field levels into a scratch history of a
@@ -218,10 +196,6 @@ Workspace carve(const Plan &p, int B, void *base)
     // split adjoint: adjoint-field history of one chunk of shots (+ the recomputed forward history of the chunk)
     if (w.split || w.split_tile) w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
     if (w.recompute) w.p_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
-    if (w.split && w.ov_clusters > 0) {
-        w.u_hist2 = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
-        if (w.recompute) w.p_hist2 = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
-    }
     w.bytes = off;
     return w;
 }
@@ -340,16 +314,6 @@ int rdfwi_plan_create(const rdfwi_survey *s, rdfwi_plan *out)
     if (e == cudaSuccess) e = upload(&p->d_r2, r2.data(), sizeof(float) * r2.size());
     if (e == cudaSuccess) e = upload(&p->d_dkap, dkap.data(), sizeof(float) * dkap.size());
     if (e == cudaSuccess) e = upload(&p->d_wavelet, p->wavelet.data(), sizeof(float) * p->wavelet.size());
-    // internal stream + events of the overlapped split adjoint: created here, never inside a call (calls may be under
-    // CUDA-graph capture).  The side stream has the highest priority so that, whenever both kernels have CTAs pending,
-    // whole clusters are placed before the imaging kernel's CTAs can fragment the GPCs.
-    if (e == cudaSuccess) {
-        int least = 0, greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        e = cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, greatest);
-        cudaEvent_t *evs[5] = {&p->ev_fork, &p->ev_adj[0], &p->ev_adj[1], &p->ev_img[0], &p->ev_img[1]};
-        for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming);
-    }
     if (e != cudaSuccess) {
         set_error(std::string("plan tables: ") + cudaGetErrorString(e));
         rdfwi_plan_destroy(reinterpret_cast<rdfwi_plan>(p));
@@ -365,9 +329,6 @@ int rdfwi_plan_destroy(rdfwi_plan plan)
     Plan *p = reinterpret_cast<Plan *>(plan);
     DeviceGuard guard(p->device);
     clear_spans(p);
-    if (p->side) cudaStreamDestroy(p->side);
-    for (cudaEvent_t ev : {p->ev_fork, p->ev_adj[0], p->ev_adj[1], p->ev_img[0], p->ev_img[1]})
-        if (ev) cudaEventDestroy(ev);
     cudaFree(p->d_isx); cudaFree(p->d_rec_ptr); cudaFree(p->d_rec_idx); cudaFree(p->d_r2); cudaFree(p->d_dkap); cudaFree(p->d_wavelet);
     delete p;
     return RDFWI_OK;
@@ -387,7 +348,6 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "timing") { clear_spans(p); p->timing = value != 0; }  // (re)starts the per-kernel-class timers
     else if (k == "u_chunk_shots") { if (value < 0) goto bad; p->u_chunk_shots = (int)value; }
     else if (k == "scratch_mb") { if (value < 0) goto bad; p->scratch_mb = value; }
-    else if (k == "adj_overlap") { if (value < -1 || value > 148) goto bad; p->adj_overlap = (int)value; }
     else if (k == "perturb") { if (value < 0 || value > 0x7fffffff) goto bad; p->perturb = (int)value; }
     else if (k == "img_prefetch") { if (value < 0 || value > 64) goto bad; p->img_prefetch = (int)value; }
     else if (k == "trace_ptr") { p->trace_ptr = reinterpret_cast<long long *>(value); }
@@ -422,8 +382,6 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
         *out = want_us ? (int64_t)(us + 0.5) : n;
     }
     else if (k == "adj_split") *out = p->last_split;
-    else if (k == "adj_overlap") *out = p->adj_overlap;
-    else if (k == "adj_overlap_used") *out = p->last_overlap;
     else if (k == "perturb") *out = p->perturb;
     else if (k == "u_chunk_shots") *out = p->u_chunk_shots;
     else if (k == "u_chunk_used") *out = p->last_u_chunk;
@@ -583,54 +541,25 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
         // split adjoint: per chunk of shots, (1) the cluster-resident kernel runs the adjoint field in the u-variable
         // and streams it to HBM, (2) a streaming kernel forms the imaging sums from the two histories
         const int nshots = B * g.ns;
-        const int ov = w.ov_clusters;
-        const_cast<Plan &>(p).last_overlap = ov;
-        // Overlapped (ov > 0): the field kernels (forward recompute, adjoint field) of chunk k+1 run on `ov` clusters on the
-        // plan's high-priority side stream while the imaging kernel of chunk k streams the two histories on the SMs that
-        // are left; scratch histories are double-buffered and chained with events (fork from / join into the caller's
-        // stream, so the whole thing is also capturable in a CUDA graph).  The imaging launches and everything after them
-        // stay on the caller's stream.
-        int sms = 148;
-        device_attr(&sms, cudaDevAttrMultiProcessorCount, p.device);
-        const int img_sms = ov > 0 ? std::max(sms - ov * cc.C, 8) : 0;
-        cudaStream_t fs = ov > 0 ? p.side : st;  // stream of the field kernels
-        if (ov > 0) {
-            RD_CUDA(cudaEventRecord(p.ev_fork, st));
-            RD_CUDA(cudaStreamWaitEvent(fs, p.ev_fork, 0));
-        }
-        int k = 0;
-        for (int s0 = 0; s0 < nshots; s0 += w.u_chunk, ++k) {
+        for (int s0 = 0; s0 < nshots; s0 += w.u_chunk) {
             const int n = std::min(w.u_chunk, nshots - s0);
-            const int buf = ov > 0 ? (k & 1) : 0;
-            float *u_hist = buf ? w.u_hist2 : w.u_hist;
-            float *p_hist = buf ? w.p_hist2 : w.p_hist;
-            const bool last = s0 + w.u_chunk >= nshots;
-            if (ov > 0 && k >= 2) RD_CUDA(cudaStreamWaitEvent(fs, p.ev_img[buf], 0));  // imaging of chunk k-2 has read this buffer
             ClusterFwdArgs a{};
             a.alpha = w.alpha; a.kap = w.kap; a.beta_src = w.beta_src;
             a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx; a.wavelet = p.d_wavelet;
             a.nshots = n; a.nt = nt; a.st = p.st; a.shot0 = s0; a.trace = p.trace_ptr;
-            a.max_clusters = (ov > 0 && k >= 1) ? ov : 0;  // the first chunk has the device to itself
             if (w.recompute) {  // forward field of the chunk, again, this time keeping every level (no seismograms)
-                a.seis = nullptr; a.hist = p_hist; a.adj_mode = 0;
-                Timed timed(p, 0, fs);
-                RD_CUDA(launch_fwd_cluster(p, cc, a, fs));
+                a.seis = nullptr; a.hist = w.p_hist; a.adj_mode = 0;
+                Timed timed(p, 0, st);
+                RD_CUDA(launch_fwd_cluster(p, cc, a, st));
             }
-            a.seis = nullptr; a.hist = u_hist; a.adj_mode = 1; a.cot = cot; a.Gb = w.Gb;
+            a.seis = nullptr; a.hist = w.u_hist; a.adj_mode = 1; a.cot = cot; a.Gb = w.Gb;
             {
-                Timed timed(p, 1, fs);
-                RD_CUDA(launch_fwd_cluster(p, cc, a, fs));
+                Timed timed(p, 1, st);
+                RD_CUDA(launch_fwd_cluster(p, cc, a, st));
             }
-            if (ov > 0) {
-                RD_CUDA(cudaEventRecord(p.ev_adj[buf], fs));
-                RD_CUDA(cudaStreamWaitEvent(st, p.ev_adj[buf], 0));
-            }
-            {
-                Timed timed(p, 2, st);
-                RD_CUDA(launch_imaging(p, w.recompute ? p_hist : hist, u_hist, w.alpha, w.kap, w.beta_src, w.Gb, w.Ga, w.Gk, s0, n,
-                                       w.recompute ? s0 : 0, (ov > 0 && !last) ? img_sms : 0, st));
-            }
-            if (ov > 0 && !last) RD_CUDA(cudaEventRecord(p.ev_img[buf], st));
+            Timed timed(p, 2, st);
+            RD_CUDA(launch_imaging(p, w.recompute ? w.p_hist : hist, w.u_hist, w.alpha, w.kap, w.beta_src, w.Gb, w.Ga, w.Gk, s0, n,
+                                   w.recompute ? s0 : 0, st));
         }
         RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
         return RDFWI_OK;
@@ -678,7 +607,7 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
                 }
             }
             Timed timed(p, 2, st);
-            RD_CUDA(launch_imaging(p, hist, w.u_hist, w.alpha, w.kap, w.beta_src, w.Gb, w.Ga, w.Gk, s0, n, 0, 0, st));
+            RD_CUDA(launch_imaging(p, hist, w.u_hist, w.alpha, w.kap, w.beta_src, w.Gb, w.Ga, w.Gk, s0, n, 0, st));
         }
         RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
         return RDFWI_OK;

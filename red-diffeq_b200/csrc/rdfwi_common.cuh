@@ -63,12 +63,7 @@ struct Plan {
     int cluster_rows = 0;   // rows marched per thread of k_fwd_cluster: 0 = auto (13; 7 or 4 on wider clusters for few shots)
     int adj_cluster_size = 0;
     int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused k_adj_cluster
-    int adj_overlap = 0;      // split adjoint: clusters left to the adjoint-field kernel while the imaging kernel of the previous
-                              // chunk runs on the other SMs (0 = auto, -1 = off: the two kernels alternate, N > 0 = N clusters)
     int perturb = 0;          // debug: seed of the schedule perturbation of k_fwd_cluster (0 = off), see rdfwi.h
-    cudaStream_t side = nullptr;       // internal high-priority stream of the overlapped split adjoint (adjoint-field kernels)
-    cudaEvent_t ev_fork = nullptr, ev_adj[2] = {nullptr, nullptr}, ev_img[2] = {nullptr, nullptr};
-    int last_overlap = 0;     // clusters the adjoint-field kernel ran on in the last overlapped backward (0 = not overlapped)
     int img_prefetch = 0;     // imaging kernel: levels ahead pulled into L2 (0 = default 4)
     long long *trace_ptr = nullptr;  // debug: device buffer for per-warp timeline stamps of k_fwd_cluster
     int last_u_chunk = 0;     // shots per chunk of the last split adjoint
@@ -81,7 +76,6 @@ struct Plan {
     int history_segment = 0;  // 0 = keep every level; K >= 3 = checkpoint pairs every K levels, recompute in the backward pass
                               // (K >= nt: no history at all -- the backward pass recomputes the forward field chunk by chunk)
     long long scratch_mb = 0; // cap on ONE scratch history of the split adjoint, MB (0 = 40000)
-    mutable int img_occ = 0;  // co-resident k_imaging CTAs per SM (asked once)
     mutable int wave_keys[8] = {0}, wave_vals[8] = {0}, wave_n = 0;  // cached fwd_cluster_wave() per configuration
     int last_fwd_C = 0, last_fwd_rows = 0;  // configuration of the last k_fwd_cluster launch (reported by rdfwi_plan_get)
 };
@@ -104,7 +98,6 @@ struct ClusterFwdArgs {
     const float *cot;       // adjoint mode: (B*ns, nt_out, nrec) cotangent of the seismograms
     float *Gb;              // adjoint mode: (B*ns) sum_t u_t[src] w_t / alpha_src
     int slabrows, ngroups, wav_smem;  // filled by launch_fwd_cluster from the ClusterConfig
-    int max_clusters;       // cap on the clusters of this launch (0 = every co-resident cluster)
     unsigned perturb;       // debug: seed of pseudo-random per-warp delays at the synchronisation points (0 = off)
 };
 
@@ -213,10 +206,9 @@ int fwd_cluster_wave(const Plan &p, const ClusterConfig &cc);  // co-resident cl
 bool adj_cluster_config(const Plan &p, ClusterConfig *cfg);
 cudaError_t launch_adj_cluster(const Plan &p, const ClusterConfig &cc, ClusterAdjArgs a, cudaStream_t st);
 // kernels_imaging.cu: zero-lag imaging sums of `nshots` shots from the forward history and the adjoint-field history
-// max_sms > 0: a persistent grid sized for that many SMs (the rest of the device is running the next chunk's adjoint field)
 cudaError_t launch_imaging(const Plan &p, const float *phist, const float *uhist, const float *alpha, const float *kap,
                            const float *beta_src, const float *Gb, float *Ga, float *Gk, int shot0, int nshots, int pshot0,
-                           int max_sms, cudaStream_t st);
+                           cudaStream_t st);
 // kernels_epilogue.cu  (planes = imaging planes per model: 1 for the per-level engine, ns for the cluster engine)
 cudaError_t launch_gradient_epilogue(const Plan &p, const float *v, int B, const float *Ga, const float *Gk,
                                      const float *Gb, int planes, const int *argmin, float *fold_tmp,

@@ -67,7 +67,7 @@ def _solve_forward(ctx, v_phys, op, need_grad):
             hist = lease.buffer
         seis = torch.empty((B, plan.ns, plan.nt_out, plan.nrec), dtype=torch.float32, device=v.device)
         ws_bytes = plan.workspace_bytes(B)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
+        ws = op._workspace(ws_bytes, v.device)
         plan.forward(v.data_ptr(), B, seis.data_ptr(), ws.data_ptr(), ws_bytes,
                      hist.data_ptr() if hist is not None else None, hist_bytes, segment, stream)
         op.last_launches = plan.last_launch_count()
@@ -96,7 +96,7 @@ def _solve_backward(ctx, grad_seis):
         # policy-owned options since this graph's forward ran -- put back what that forward decided
         ctx.op._apply_policy(plan, ctx.policy)
         ws_bytes = plan.workspace_bytes(B)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
+        ws = ctx.op._workspace(ws_bytes, v.device)
         plan.backward(v.data_ptr(), B, g.data_ptr(), grad_v.data_ptr(), ws.data_ptr(), ws_bytes,
                       hist.data_ptr() if hist is not None else None, ctx.hist_bytes, ctx.segment, stream)
         ctx.op.last_launches += plan.last_launch_count()
@@ -183,6 +183,7 @@ class FWIForward(nn.Module):
         self.ctx = _survey.complete_ctx(ctx, sample_spatial)
         self._plans = {}
         self._history_arena = {}
+        self._ws = {}
         self._segment = None
         self._segment_auto = {}
         self._lock = threading.Lock()
@@ -258,6 +259,8 @@ class FWIForward(nn.Module):
         if policy is None:
             free, _total = torch.cuda.mem_get_info(device)
             idle = sum(b.numel() for b in self._history_arena.get(str(device), []))
+            held = self._ws.get(str(device))
+            idle += held.numel() if held is not None else 0   # the workspace is re-used (or replaced) by the next call
             budget = 0.9 * (free + idle + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device))
 
             def fits(cand):
@@ -318,11 +321,30 @@ class FWIForward(nn.Module):
                 f"{(free + reserved_free) / 2**30:.1f} GiB is available; reduce the batch")
         return _HistoryLease(arena, torch.empty(nbytes, dtype=torch.uint8, device=device))
 
+    def _workspace(self, nbytes, device):
+        """The library's scratch for one call (coefficient planes, imaging planes, the scratch histories of the split
+        adjoint: up to tens of GB).  Owned by the operator and reused by every call: nothing in it outlives a call (each
+        call recomputes its coefficient planes), calls of one operator are ordered on the stream autograd runs them on, and
+        a buffer that keeps its address is what CUDA-graph replays need.  Allocating it per call let the caching allocator
+        split the freed block (a 33 GB request failed with 33 GB cached but fragmented, round 2)."""
+        key = str(device)
+        with self._lock:
+            buf = self._ws.get(key)
+            if buf is None or buf.numel() < nbytes:
+                self._ws[key] = None
+                del buf
+                if not torch.cuda.is_current_stream_capturing():
+                    torch.cuda.empty_cache() if nbytes > (1 << 30) else None
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                self._ws[key] = buf
+        return buf
+
     def release_memory(self):
-        """Drop the idle wavefield-history buffers held for reuse."""
+        """Drop the idle wavefield-history buffers and the workspace held for reuse."""
         with self._lock:
             for arena in self._history_arena.values():
                 arena.clear()
+            self._ws.clear()
 
     # -- the operator -----------------------------------------------------------------------------
     def forward(self, v):
