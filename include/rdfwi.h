@@ -64,14 +64,15 @@ int rdfwi_plan_destroy(rdfwi_plan plan);
 
 /* Tunables (all optional).  Keys:
  *   "engine"         0 = by problem size (default), 1 = per-level tiled kernels, 2 = cluster-resident time loop
- *   "adj_mode"       0 = split adjoint (adjoint-field kernel + streaming imaging kernel; default), 1 = fused adjoint
+ *   "adj_mode"       0 = split adjoint (adjoint-field kernel + streaming imaging kernel; default), 1 = fused per-level
+ *                    adjoint (one launch per level, imaging sums read-modify-written in HBM; needs no scratch history)
  *   "history_segment" 0 = keep every level; K >= 3 = keep a pair of levels every K levels and recompute K levels at a
  *                    time in the backward pass; K >= nt = keep nothing, the backward pass recomputes the forward field
  *                    chunk by chunk (must be set BEFORE the workspace / history sizes are queried; the `segment`
  *                    argument of forward/backward must equal it)
  *   "u_chunk_shots"  shots per chunk of the split adjoint (0 = auto: whole waves of co-resident clusters)
  *   "scratch_mb"     cap on one scratch history of the split adjoint, MB (0 = 40000; 55000 for the recompute tier)
- *   "cluster_size" / "adj_cluster_size"  CTAs per cluster of the cluster-resident kernels (0 = smallest of 1..8 that fits)
+ *   "cluster_size"   CTAs per cluster of the cluster-resident time loop (0 = smallest of 1..8 that fits)
  *   "cluster_rows"   rows marched per thread by the cluster-resident time loop: 13, 7 or 4 (0 = auto: 13, or 7 / 4 on a
  *                    wider cluster when a launch has so few shots that each still gets its own co-resident cluster)
  *   "rows_per_thread" (1, 2, 4, 8; tile rows = 8x) / "adj_rows_per_thread"  z-rows marched per thread, per-level kernels
@@ -84,9 +85,9 @@ int rdfwi_plan_destroy(rdfwi_plan plan);
  *                    of the cluster-resident time loop -- halo waits, early / late halo pushes, bulk-copy hand-over, sampling
  *                    warp -- run by separate kernel instantiations; results must not change (tests/test_gpu_perturb.py: the
  *                    substitute for racecheck, which is closed on the GPU pool).  0 = off (production kernels)
- * rdfwi_plan_get additionally answers "pitch", "nzp", "nxp", "nt_out", "cluster_size_used", "adj_cluster_size_used", "cluster_size_last", "cluster_rows_last" (what the
+ * rdfwi_plan_get additionally answers "pitch", "nzp", "nxp", "nt_out", "cluster_size_used", "cluster_size_last", "cluster_rows_last" (what the
  * last cluster-resident launch ran),
- * "cluster_wave" (co-resident clusters of the forward configuration), "adj_split" (what the last backward ran: 0 fused,
+ * "cluster_wave" (co-resident clusters of the forward configuration), "adj_split" (what the last backward ran: 0 per-level fused,
  * 1 cluster split, 2 cluster split on a recomputed forward history, 3 per-level split), "u_chunk_used". */
 int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value);
 int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *value_out);

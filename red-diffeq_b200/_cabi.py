@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.environ.get("RDFWI_LIB") or os.path.join(_PKG, "librdfwi.so")   # RDFWI_LIB: A/B builds of the same sources
-SOURCES = ["rdfwi_api.cu", "kernels_prologue.cu", "kernels_step.cu", "kernels_tile.cu", "kernels_cluster.cu", "kernels_cluster_adj.cu", "kernels_imaging.cu", "kernels_epilogue.cu", "kernels_misfit.cu"]
+SOURCES = ["rdfwi_api.cu", "kernels_prologue.cu", "kernels_step.cu", "kernels_tile.cu", "kernels_cluster.cu", "kernels_imaging.cu", "kernels_epilogue.cu", "kernels_misfit.cu"]
 HEADERS = [os.path.join(_CSRC, "rdfwi_common.cuh"), os.path.join(_CSRC, "cluster_ptx.cuh"), os.path.join(_ROOT, "include", "rdfwi.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
               "-Xcompiler", "-fPIC", "-shared"]

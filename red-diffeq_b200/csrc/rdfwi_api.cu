@@ -111,7 +111,6 @@ struct Workspace {
     int g_planes = 1;
     float *seg_hist = nullptr;
     bool split = false;
-    bool fused = false;       // fused cluster-resident adjoint (k_adj_cluster) when the split adjoint is not used
     bool split_tile = false;  // split adjoint on the per-level engine: tiled adjoint-field levels + streaming imaging
     bool recompute = false;   // split adjoint on a forward history recomputed chunk by chunk (history_segment >= nt)
     int u_chunk = 0;
@@ -142,20 +141,19 @@ Workspace carve(const Plan &p, int B, void *base)
     w.minpart = (float *)take((size_t)B * kMinBlocks * 2 * 4);
     w.fields = (float *)take(3 * w.chunk_level * 4);
     w.zero = (float *)take(w.chunk_level * 4);
-    ClusterConfig acc, fcc;
-    // split adjoint (cluster u-field kernel + streaming imaging kernel) whenever the forward cluster kernel fits;
-    // else the fused cluster adjoint; histories checkpointed in time run on the per-level engine.  history_segment >= nt
-    // (a single segment: nothing is kept) runs the split adjoint on a forward history recomputed chunk by chunk.
+    ClusterConfig fcc;
+    // split adjoint (cluster u-field kernel + streaming imaging kernel) whenever the forward cluster kernel fits; histories
+    // checkpointed in time and adj_mode = 1 run the per-level adjoint.  history_segment >= nt (a single segment: nothing is
+    // kept) runs the split adjoint on a forward history recomputed chunk by chunk.
     const bool single_segment = p.history_segment >= p.nt;
     const bool cluster_ok = p.engine != 1 && (p.history_segment == 0 || single_segment);
-    const bool fused_ok = cluster_ok && !single_segment && cluster_config(p, &fcc) && adj_cluster_config(p, &acc);  // (cluster forward too)
     w.split = cluster_ok && (p.adj_mode == 0 || single_segment) && cluster_config(p, &fcc);
     w.recompute = w.split && single_segment;
     w.u_chunk = 0;
     if (w.split) {
         // Shots whose adjoint-field history is in flight at once: whole waves of co-resident clusters (33 four-CTA or 24
-        // six-CTA clusters per wave), two waves when the scratch cap allows, evened out over the chunks; long records
-        // that leave less than a wave per chunk use the fused kernel when that exists.
+        // six-CTA clusters per wave), two waves when the scratch cap allows, evened out over the chunks (long records that
+        // leave less than a wave per chunk are better served by history_segment >= nt: the operator's policy picks that).
         const int nshots = B * g.ns;
         const int wave = cached_wave(p, fcc);
         const double per_shot = (double)p.nt * (double)g.level * sizeof(float);
@@ -169,12 +167,10 @@ Workspace carve(const Plan &p, int B, void *base)
         chunk = std::min(chunk, nshots);
         const int nchunks = (nshots + chunk - 1) / chunk;
         w.u_chunk = (nshots + nchunks - 1) / nchunks;
-        if (p.u_chunk_shots == 0 && !single_segment && w.u_chunk < nshots && w.u_chunk < wave && fused_ok) { w.split = false; w.u_chunk = 0; }
     }
-    w.fused = fused_ok && !w.split;
     // per-level engine, every level kept: the adjoint is split too (tiled adjoint-field levels into a scratch history of a
     // chunk of shots, then the pointwise imaging kernel); adj_mode = 1 keeps the fused per-level adjoint
-    w.split_tile = !w.split && !w.fused && p.history_segment == 0 && p.adj_mode == 0;
+    w.split_tile = !w.split && p.history_segment == 0 && p.adj_mode == 0;
     if (w.split_tile) {
         const int nshots = B * g.ns;
         const double per_shot = (double)p.nt * (double)g.level * sizeof(float);
@@ -185,7 +181,7 @@ Workspace carve(const Plan &p, int B, void *base)
         w.u_chunk = (nshots + nchunks - 1) / nchunks;
     }
     // imaging planes per model: one per shot for the cluster engines, one per grid.z slice for the per-level adjoint
-    w.g_planes = (w.split || fused_ok || w.split_tile) ? g.ns : adj_shot_slices(p, w.nb);
+    w.g_planes = (w.split || w.split_tile) ? g.ns : adj_shot_slices(p, w.nb);
     w.Ga = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gk = (float *)take((size_t)B * w.g_planes * g.level * 4);
     w.Gb = (float *)take((size_t)B * g.ns * 4);
@@ -353,7 +349,6 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "trace_ptr") { p->trace_ptr = reinterpret_cast<long long *>(value); }
     else if (k == "cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->cluster_size = (int)value; }
     else if (k == "cluster_rows") { if (value != 0 && value != 4 && value != 7 && value != kClusterRowsMax) goto bad; p->cluster_rows = (int)value; }
-    else if (k == "adj_cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->adj_cluster_size = (int)value; }
     else { set_error("unknown option " + k); return RDFWI_EINVAL; }
     return RDFWI_OK;
 bad:
@@ -392,7 +387,6 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
     else if (k == "cluster_size_last") *out = p->last_fwd_C;
     else if (k == "cluster_rows_last") *out = p->last_fwd_rows;
     else if (k == "cluster_size_used") { ClusterConfig cc; *out = cluster_config(*p, &cc) ? cc.C : 0; }
-    else if (k == "adj_cluster_size_used") { ClusterConfig cc; *out = adj_cluster_config(*p, &cc) ? cc.C : 0; }
     else if (k == "pitch") *out = p->g.pitch;
     else if (k == "nzp") *out = p->g.nzp;
     else if (k == "nxp") *out = p->g.nxp;
@@ -564,20 +558,7 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
         RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
         return RDFWI_OK;
     }
-    if (!ckpt && w.fused && adj_cluster_config(p, &cc)) {
-        // cluster-resident reverse-time loop: one launch for all shots and all levels
-        ClusterAdjArgs a{};
-        a.alpha = w.alpha; a.kap = w.kap; a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx;
-        a.wavelet = p.d_wavelet; a.cot = cot; a.hist = hist; a.Ga = w.Ga; a.Gk = w.Gk; a.Gb = w.Gb;
-        a.nshots = B * g.ns; a.nt = nt; a.st = p.st;
-        {
-            Timed timed(p, 3, st);
-            RD_CUDA(launch_adj_cluster(p, cc, a, st));
-        }
-        RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
-        return RDFWI_OK;
-    }
-    if (p.engine == 2 && !ckpt) { set_error("engine=2 (cluster-resident) requested but the adjoint slabs do not fit a cluster"); return RDFWI_EINVAL; }
+    if (p.engine == 2 && !ckpt && p.adj_mode == 0) { set_error("engine=2 (cluster-resident) requested but the grid does not fit a cluster"); return RDFWI_EINVAL; }
     RD_CUDA(cudaMemsetAsync(w.zero, 0, w.chunk_level * sizeof(float), st));
     if (!ckpt && w.split_tile) {
         // split adjoint on the per-level engine: per chunk of shots, nt tiled launches write the adjoint field u_t (slot k

@@ -61,8 +61,7 @@ struct Plan {
     int engine = 0;         // 0 = auto, 1 = per-level kernels, 2 = cluster-resident time loop
     int cluster_size = 0;   // 0 = smallest cluster that fits
     int cluster_rows = 0;   // rows marched per thread of k_fwd_cluster: 0 = auto (13; 7 or 4 on wider clusters for few shots)
-    int adj_cluster_size = 0;
-    int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused k_adj_cluster
+    int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused per-level adjoint (k_adj_step)
     int perturb = 0;          // debug: seed of the schedule perturbation of k_fwd_cluster (0 = off), see rdfwi.h
     int img_prefetch = 0;     // imaging kernel: levels ahead pulled into L2 (0 = default 4)
     long long *trace_ptr = nullptr;  // debug: device buffer for per-warp timeline stamps of k_fwd_cluster
@@ -99,23 +98,6 @@ struct ClusterFwdArgs {
     float *Gb;              // adjoint mode: (B*ns) sum_t u_t[src] w_t / alpha_src
     int slabrows, ngroups, wav_smem;  // filled by launch_fwd_cluster from the ClusterConfig
     unsigned perturb;       // debug: seed of pseudo-random per-warp delays at the synchronisation points (0 = off)
-};
-
-// Cluster-resident reverse-time loop (kernels_cluster_adj.cu).
-struct ClusterAdjArgs {
-    const float *alpha;    // (B, nzp, pitch)
-    const float *kap;      // (B, nbc+1)
-    const int *isx;
-    const int *rec_ptr;
-    const int *rec_idx;
-    const float *wavelet;  // (nt) device
-    const float *cot;      // (B*ns, nt_out, nrec)
-    const float *hist;     // [shot][t][z][x], t = 0..nt-2
-    float *Ga;             // (B*ns, nzp, pitch) per-shot imaging sums (already divided by alpha)
-    float *Gk;             // (B*ns, nzp, pitch)
-    float *Gb;             // (B*ns)
-    int nshots, nt, st;
-    int slabrows, ngroups, wav_smem;  // filled by the launcher from the ClusterConfig
 };
 
 struct ClusterConfig {
@@ -202,9 +184,6 @@ int adj_shot_slices(const Plan &p, int nb);  // imaging planes per model the per
 bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots = 0);
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st);
 int fwd_cluster_wave(const Plan &p, const ClusterConfig &cc);  // co-resident clusters = shots in flight per wave
-// kernels_cluster_adj.cu
-bool adj_cluster_config(const Plan &p, ClusterConfig *cfg);
-cudaError_t launch_adj_cluster(const Plan &p, const ClusterConfig &cc, ClusterAdjArgs a, cudaStream_t st);
 // kernels_imaging.cu: zero-lag imaging sums of `nshots` shots from the forward history and the adjoint-field history
 cudaError_t launch_imaging(const Plan &p, const float *phist, const float *uhist, const float *alpha, const float *kap,
                            const float *beta_src, const float *Gb, float *Ga, float *Gk, int shot0, int nshots, int pshot0,

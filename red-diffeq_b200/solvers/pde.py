@@ -248,7 +248,7 @@ class FWIForward(nn.Module):
         Automatic mode walks the tiers until the buffers fit the free HBM: (1) every level + split adjoint (needs a
         scratch history of the adjoint field); (2) no history at all: the backward pass recomputes the forward field
         chunk by chunk on the cluster engine (segment = nt, one extra forward, two scratch histories of one or two waves
-        of shots); (3) every level + fused cluster adjoint (no scratch); (4) history checkpointed in time on the
+        of shots); (3) every level + fused per-level adjoint (no scratch); (4) history checkpointed in time on the
         per-level engine."""
         if self._segment is not None:
             policy = (self._segment, {})
@@ -273,8 +273,8 @@ class FWIForward(nn.Module):
             wave = plan.get("cluster_wave") if clustered else 0
             tiers = [(0, {})]
             if clustered and "adj_mode" not in user:
-                # a record so long that the scratch history of the split adjoint holds less than a wave of shots makes
-                # the library fall back to the fused adjoint kernel: recomputing is faster than that
+                # a record so long that the scratch history of the split adjoint holds less than a wave of shots leaves
+                # most SMs idle in every chunk: recomputing the forward field chunk by chunk is faster than that
                 per_shot = 4.0 * plan.nt * plan.level_floats()
                 if int(40e9 // per_shot) < min(wave, B * plan.ns):
                     tiers = []

@@ -61,7 +61,7 @@ def test_gradient_matches_reference(golden):
 @pytest.mark.parametrize("name", ["tiny_default", "tiny_custom", "tiny_half_receivers"])
 @pytest.mark.parametrize("rows", [1, 2, 4, 8])
 @pytest.mark.parametrize("chunk", [0, 1])
-@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "cluster-split", "cluster-fused"])
+@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "cluster-split", "cluster+per-level-fused"])
 def test_kernel_variants_agree_with_oracle(name, rows, chunk, engine, oracle):
     if not engine.startswith("per-level") and (rows != 1 or chunk != 0):
         pytest.skip("rows/chunk only affect the per-level engine")
@@ -174,7 +174,7 @@ def test_few_shots_pick_a_wide_cluster():
     assert np.array_equal(s16[3:4], s)
 
 
-@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "per-level-checkpointed", "cluster-split", "cluster-fused"])
+@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "per-level-checkpointed", "cluster-split", "cluster+per-level-fused"])
 def test_many_shots_per_model(engine, oracle):
     """More shots than any golden case (ns = 11: the per-level adjoint deals them over several grid.z slices, each with its
     own imaging plane; the cluster engines run more shots than fit one chunk)."""
@@ -317,7 +317,7 @@ def test_errors():
 
 
 @pytest.mark.parametrize("nx,nbc", [(15, 9), (17, 9), (21, 10), (16, 8)])
-@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "cluster-split", "cluster-fused"])
+@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "cluster-split", "cluster+per-level-fused"])
 def test_odd_widths_against_oracle(nx, nbc, engine, oracle):
     """Padded widths with nxp % 4 in {1, 3, 0, ...}: the periodic image columns of the pitched layout (1..3 of them)
     must reproduce torch.roll's wrap-around bit for bit; no reference fixture has such a width, so the pinned oracle checks."""

@@ -74,8 +74,7 @@ def run_case(n, ns, B, nt, peak, dev, rank, world):
     clustered = plan.get("cluster_size_used") and OPTS.get("engine") != 1
     sp = plan.get("adj_split")
     eng_f = "cluster C=%d R=%d" % (plan.get("cluster_size_last"), plan.get("cluster_rows_last")) if clustered and (not seg or sp == 2) else "per-level"
-    eng_a = {1: "cluster split", 2: "cluster split, forward recomputed", 3: "per-level split (chunks of %d shots)" % plan.get("u_chunk_used")}.get(sp) or \
-        (("cluster fused C=%d" % plan.get("adj_cluster_size_used")) if plan.get("adj_cluster_size_used") and not seg and OPTS.get("engine") != 1 else "per-level fused")
+    eng_a = {1: "cluster split", 2: "cluster split, forward recomputed", 3: "per-level split (chunks of %d shots)" % plan.get("u_chunk_used")}.get(sp) or "per-level fused"
     op.release_memory()
     hist = "none (recomputed)" if sp == 2 else ("checkpoint K=%d" % seg if seg else "full")
     return dict(n=n, ns=ns, B=B, nt=nt, forward_ms=f_ms, adjoint_ms=a_ms, pairs_per_s=rate, frac=rate * 28 / (world * peak * 1e9),
