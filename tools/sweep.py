@@ -27,7 +27,7 @@ CASES = [  # (n, ns, B, nt)
     (70, 5, 1, 1000), (70, 5, 64, 1000), (128, 1, 1, 1000), (128, 16, 1, 1000), (128, 64, 1, 1000), (128, 256, 1, 1000),
     (256, 16, 1, 1000), (256, 64, 1, 1000), (256, 256, 1, 1000), (512, 4, 1, 1000), (512, 16, 1, 1000), (512, 64, 1, 1000),
     (1024, 4, 1, 1000), (1024, 16, 1, 1000), (2048, 4, 1, 500), (2048, 16, 1, 500), (4096, 1, 1, 300), (4096, 4, 1, 300),
-    (4096, 16, 1, 100),
+    (4096, 16, 1, 150),
 ]
 
 

@@ -13,7 +13,7 @@ trace = torch.zeros((16, 4, 16, 6), dtype=torch.int64, device="cuda:0")   # [cta
 op.set_option("trace_ptr", trace.data_ptr())
 v = torch.tensor(synthetic.velocity_models(B, nz, nx), device="cuda:0", requires_grad=True)
 s = op(v); torch.cuda.synchronize()
-C = op._plan_for(nz, nx, torch.device("cuda:0")).get("cluster_size_used")
+C = op._plan_for(nz, nx, torch.device("cuda:0")).get("cluster_size_last")   # what the launch ran (wide clusters for few shots)
 if mode == "adj":      # trace the adjoint-field launch (k_fwd_cluster<ADJ>) instead
     trace.zero_()
     s.backward(torch.ones_like(s)); torch.cuda.synchronize()
