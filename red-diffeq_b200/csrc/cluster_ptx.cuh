@@ -117,6 +117,78 @@ struct HaloPush {             // per thread
     int bar;                  // 0 = the receiver's "top halo" barrier, 1 = its "bottom halo" barrier
 };
 
+// ---- tensor memory as a per-thread scratchpad (imaging accumulators of the resident adjoint).
+// TMEM is 128 lanes x 512 columns of 32 bits per SM.  A warp can only touch the 32 lanes 32*(warp%4) .. +31, thread i of
+// the warp lane 32*(warp%4)+i, so with 16 warps per CTA every thread privately owns 128 columns: [128*(warp/4), +128).
+// Measured (tools/tmem_bench.cu, profiles/tmem_scratchpad_r2.txt): 270 B/clk/SM loads, 350 B/clk/SM stores -- twice the
+// shared-memory pipe -- and a read-modify-write stream next to a saturating LDS/STS stream slows the latter by 10 %:
+// the two are separate pipes.  Addresses are warp-uniform: bits 31:16 lane, 15:0 column.
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, float (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tm_st4(uint32_t taddr, float a, float b, float c, float d)
+{
+    // no "memory" clobber: tensor memory is its own address space, and a clobber here would pin every shared-memory access
+    // of the sweep to its row (the compiler could no longer hoist the next row's loads above this row's arithmetic)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+// wait for the thread's outstanding tcgen05.ld; the loaded registers pass through the statement ("+f") so that no use of
+// them can be scheduled above it -- the only ordering the compiler has to respect
+__device__ __forceinline__ void tm_wait_ld(float (&a)[4], float (&b)[4])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]));
+}
+__device__ __forceinline__ void tm_wait_ld(float (&a)[4], float (&b)[4], float (&c)[4])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(c[0]), "+f"(c[1]),
+                   "+f"(c[2]), "+f"(c[3]));
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// whole-TMEM allocation by one warp (one CTA per SM: the slabs fill the shared memory); base address lands in *slot
+__device__ __forceinline__ void tm_alloc_all(uint32_t *slot)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tm_free_all(uint32_t base)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+}
+__device__ __forceinline__ void tm_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 16-byte asynchronous copy global -> shared (L2 only), one commit group per copy; volatile statements keep their order
+// among themselves (copy -> wait -> read of the slot -> next copy into it), no "memory" clobber for the reason above
+__device__ __forceinline__ void cp_async16_commit(uint32_t saddr, const float *gptr)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" ::"r"(saddr), "l"(gptr));
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+__device__ __forceinline__ float4 lds4_volatile(uint32_t saddr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const float *gptr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
+// per-thread state of the resident imaging (k_fwd_cluster, MODE 2)
+struct ImgThread {
+    const float *pg;  // global: this thread's float4 of its first marching row of the forward level paired with this sweep
+    uint32_t tm;      // TMEM address of the thread's columns: Ga [0, 4R), Gk [4R, 8R), alpha of the last ATM rows [8R, ..)
+    float *ring;      // the thread's first 16-byte slot in shared memory (the second one is `threads` slots further)
+};
+
 // ---- mbarrier + bulk load (global -> shared), used to stream the forward history into the adjoint
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {

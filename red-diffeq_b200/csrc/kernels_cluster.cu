@@ -38,11 +38,23 @@ namespace {
 //   * two sweep instantiations (down / up) still fit the instruction cache; four (x two buffer roles) did
 //     not (ncu: stall_no_instruction), so buffer roles are runtime base pointers.
 
-template <int RMAX, int PITCH, int DIR, bool EXACT>
+// IMG (resident imaging, MODE 2 of k_fwd_cluster): the sweep that produces u_t also adds this level's terms of the zero-lag
+// imaging sums (kernels_imaging.cu has the formulas) for the thread's cells,
+//     ga += p_t [ u_t - (2-kappa) u_{t+1} + (1-kappa) u_{t+2} ],      gk += p_t [ u_{t+2} - u_{t+1} ],
+// with u_t = the row just computed, u_{t+1} its centre operand, u_{t+2} the value it overwrites.  The 8 accumulators per
+// float4 live in TENSOR MEMORY -- 104 of the thread's 128 private columns -- because the register file is full (alpha alone
+// is 52 registers); ATM > 0: alpha of the last ATM marching rows lives there as well and is read with the accumulators.
+// p_t comes from the forward history in HBM.  Loaded into registers (LDG two rows ahead) ptxas sinks every load to ~10
+// instructions before its first use whatever the source order, and the sweep waits a full L2 / HBM latency per row
+// (65 ms per 64 models, 40 ms with the loads removed: profiles/resident_adjoint_r2.md).  So each thread owns two 16-byte
+// slots in shared memory and fills them with cp.async two rows ahead: asynchronous, no registers, no scheduler to argue
+// with; the slab of the level three sweeps ahead is pulled into L2 by one bulk prefetch per level.
+constexpr int kImgPrefetchLevels = 3;
+template <int RMAX, int PITCH, int DIR, bool EXACT, bool IMG, int ATM>
 __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cur, const int prv, const int kap_off,
                                           const int pitch_rt, const int l0, const SweepThread &th,
                                           const float4 (&al)[RMAX], const float (&kapx)[4], const HaloPush &hp,
-                                          const uint64_t *push_bar, const bool push_now)
+                                          const uint64_t *push_bar, const bool push_now, const ImgThread &im)
 {
     const int pitch = PITCH > 0 ? PITCH : pitch_rt;
     const int P = DIR * pitch;                                     // signed row step in marching order
@@ -54,10 +66,28 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
     const float *kz = smem + kap_off + l0;
     const float *push_dst = smem + prv + hp.dst + th.x;
     const int nvalid = th.lb - th.la;
+    // forward-history rows of the thread, two in flight (rows the thread does not own re-read its first row: in bounds)
+    const uint32_t ring0 = IMG ? smem_u32(im.ring) : 0, ring1 = ring0 + kClusterThreads * 16;
+    if (IMG) {  // rows the thread does not own re-read its first row (in bounds); their sums are never written out
+        cp_async16_commit(ring0, im.pg);
+        cp_async16_commit(ring1, im.pg + (1 < nvalid ? P : 0));
+    }
 
     float4 w0 = ld4(cb - 2 * P), w1 = ld4(cb - P), w2 = ld4(cb), w3 = ld4(cb + P);
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
+        float ga[4], gk[4], alt[4];
+        float4 pv;
+        if (IMG) {
+            tm_ld4(im.tm + 4 * r, ga);
+            tm_ld4(im.tm + 4 * RMAX + 4 * r, gk);
+            if (r >= RMAX - ATM) tm_ld4(im.tm + 8 * RMAX + 4 * (r - (RMAX - ATM)), alt);
+            const uint32_t slot = (r & 1) ? ring1 : ring0;
+            if (r + 1 < RMAX) cp_async_wait<1>();  // this row's copy has landed (the next row's may be in flight)
+            else cp_async_wait<0>();
+            pv = lds4_volatile(slot);
+            if (r + 2 < RMAX) cp_async16_commit(slot, im.pg + (r + 2 < nvalid ? (r + 2) * P : 0));
+        }
         const float4 w4 = ld4(cb + (r + 2) * P);
         const float4 old = ld4(pb + r * P);
         const float kapz = kz[DIR * r];
@@ -81,6 +111,11 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
         }
         const float e[8] = {l2, l1, w2.x, w2.y, w2.z, w2.w, r0, r1};
         float o[4];
+        if (IMG) {
+            if (r >= RMAX - ATM) tm_wait_ld(ga, gk, alt);
+            else tm_wait_ld(ga, gk);
+        }
+        const float4 alr = (IMG && r >= RMAX - ATM) ? make_float4(alt[0], alt[1], alt[2], alt[3]) : al[r];
         // Two cells per instruction for the twelve additions of a cell (FADD2, IEEE round-to-nearest per lane, same
         // association as the reference); the six multiplications stay scalar so that ptxas cannot contract them
         // into FFMA2 (it does contract packed products, even with .rn) -- seismograms stay bit-identical.
@@ -92,7 +127,7 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             const float2 up2 = h ? make_float2(w0.z, w0.w) : make_float2(w0.x, w0.y);
             const float2 dn2 = h ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);
             const float2 oldp = h ? make_float2(old.z, old.w) : make_float2(old.x, old.y);
-            const float2 alp = h ? make_float2(al[r].z, al[r].w) : make_float2(al[r].x, al[r].y);
+            const float2 alp = h ? make_float2(alr.z, alr.w) : make_float2(alr.x, alr.y);
             // (((p1[z-1] + p1[z+1]) + p1[x-1]) + p1[x+1]) and the same at distance 2   (:79; + is commutative)
             const float2 s1 = f2add(f2add(f2add(up1, dn1), make_float2(e[j + 1], e[j + 2])), make_float2(e[j + 3], e[j + 4]));
             const float2 s2 = f2add(f2add(f2add(up2, dn2), make_float2(e[j], e[j + 1])), make_float2(e[j + 4], e[j + 5]));
@@ -115,14 +150,26 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
                 const float2 t1 = f2sub(f2fma(make_float2(-5.0f, -5.0f), alp, make_float2(2.0f, 2.0f)), kp);
                 const float2 t2 = f2sub(make_float2(1.0f, 1.0f), kp);
                 res = f2fma(alp, lap, f2sub(f2mul(t1, cen), f2mul(t2, oldp)));
+                if (IMG) {  // same expression tree as k_imaging: p * ((u - (2-k) u1) + (1-k) u2), p * (u2 - u1)
+                    const float2 pp = h ? make_float2(pv.z, pv.w) : make_float2(pv.x, pv.y);
+                    const float2 br = f2fma(t2, oldp, f2fma(f2sub(kp, make_float2(2.0f, 2.0f)), cen, res));
+                    const float2 na = f2fma(pp, br, make_float2(ga[j], ga[j + 1]));
+                    const float2 nk = f2fma(pp, f2sub(oldp, cen), make_float2(gk[j], gk[j + 1]));
+                    ga[j] = na.x; ga[j + 1] = na.y; gk[j] = nk.x; gk[j + 1] = nk.y;
+                }
             }
             o[j] = res.x; o[j + 1] = res.y;
+        }
+        if (IMG) {
+            tm_st4(im.tm + 4 * r, ga[0], ga[1], ga[2], ga[3]);
+            tm_st4(im.tm + 4 * RMAX + 4 * r, gk[0], gk[1], gk[2], gk[3]);
         }
         const float4 out = make_float4(o[0], o[1], o[2], o[3]);
         if (r < nvalid) st4(pb + r * P, out);  // marching rows 0 .. nvalid-1 are the thread's own (both directions)
         if (r < 2 && push_now) st_async_v4(push_dst + r * P, push_bar, hp.cta, out);  // edge rows leave at once
         w0 = w1; w1 = w2; w2 = w3; w3 = w4;
     }
+    if (IMG) tm_wait_st();  // the accumulators are read again a level later
 }
 
 // ADJ = false: forward wavefield p (source injection, receiver sampling -> seismograms, history of p).
@@ -151,11 +198,21 @@ __device__ __forceinline__ void jitter(const unsigned seed, const unsigned site,
     if (PERT) jitter_sleep(seed, site, t);
 }
 
-template <int RMAX, int PITCH, bool ADJ, bool PERT>
+// MODE = 2: the adjoint field as in MODE 1, but nothing is written to HBM per level: the imaging sums are formed inside the
+//              sweep from the forward history (see fwd_sweep) and the kernel writes the per-shot planes Ga, Gk at the end of
+//              a shot.  Replaces adjoint-field kernel + u-history + k_imaging (12 B of HBM traffic per cell-update) by one
+//              kernel reading 4 B.  The cotangent injected at the receiver cells after the sweep is not in the row the sweep
+//              saw; its share, sum_t p_t[rec] g_t, is kept per column in shared memory by the CTA's last warp (s_ginj).
+template <int RMAX, int PITCH, int MODE, bool PERT>
 __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdArgs a, Grid g)
 {
     constexpr int NT = kClusterThreads;
+    constexpr bool ADJ = MODE >= 1, IMG = MODE == 2;
+    // alpha rows kept in tensor memory beside the 8 accumulator columns per row (128 columns per thread)
+    constexpr int ATM = !IMG ? 0 : ((128 - 8 * RMAX) / 4 < RMAX ? (128 - 8 * RMAX) / 4 : RMAX);
+    static_assert(!IMG || 8 * RMAX + 4 * ATM <= 128, "tensor-memory columns per thread");
     extern __shared__ __align__(128) float smem[];
+    __shared__ uint32_t s_tmem;
 
     const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
     const int cid = blockIdx.x / C, ncl = gridDim.x / C;
@@ -173,12 +230,15 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ((kap_off + a.slabrows + 3) & ~3));
     // small read-only tables staged once per kernel so the epilogue never waits on global memory:
     // receiver CSR (columns -> receiver slots) and, when it fits, the wavelet
-    int *s_rec_ptr = reinterpret_cast<int *>(bars + 4);
+    float *s_prow = reinterpret_cast<float *>(bars + 4);  // [2][pitch] receiver row of the forward level (MODE 2), 16-byte aligned
+    float *s_ginj = s_prow + 2 * pitch;                   // [pitch] sum_t p_t[rec] g_t per column (MODE 2)
+    int *s_rec_ptr = reinterpret_cast<int *>(s_ginj + pitch);
     int *s_rec_idx = s_rec_ptr + g.nxp + 1;
     float *s_cot = reinterpret_cast<float *>(s_rec_idx + g.nrec);  // [2][nxp] per-column cotangent sums (adjoint mode)
     float *s_raw = s_cot + 2 * g.nxp;  // [2][nrec] cotangent rows as they sit in HBM, landed by cp.async (adjoint mode)
     float *s_wav = s_raw + 2 * g.nrec;
-    const bool wav_in_smem = a.wav_smem != 0;
+    const bool wav_in_smem = a.wav_smem != 0;  // (never in MODE 2: the ring takes the room)
+    float *s_ring = smem + (((int)(s_wav - smem) + 3) & ~3);  // MODE 2: [2][threads] 16-byte slots, see fwd_sweep
     const bool st1 = a.st == 1;  // every level is sampled (all configs of the reference): no integer division on the level's critical path
 
     const int tid = threadIdx.x, lane_id = tid & 31;
@@ -247,6 +307,17 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
     }
+    uint32_t tm = 0;
+    if (IMG) {
+        if (tid < 32) tm_alloc_all(&s_tmem);
+        tm_fence_before_sync();
+        __syncthreads();
+        tm_fence_after_sync();
+        tm = s_tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * 128);
+#pragma unroll
+        for (int c = 0; c < 8 * RMAX; c += 4) tm_st4(tm + c, 0.f, 0.f, 0.f, 0.f);
+        tm_wait_st();
+    }
     for (int i = tid; i <= g.nxp; i += NT) s_rec_ptr[i] = a.rec_ptr[i];
     for (int i = tid; i < g.nrec; i += NT) s_rec_idx[i] = a.rec_idx[i];
     if (wav_in_smem)
@@ -264,12 +335,15 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
             const int kz = sponge_index(r0 + i, g.nzp, g.nbc);
             smem[kap_off + i] = (i < nrows && kz >= 0) ? kap_b[kz] : 0.0f;
         }
-        float4 al[RMAX];  // alpha of the thread's rows, in marching order
+        float4 al[RMAX];  // alpha of the thread's rows, in marching order (MODE 2: the last ATM rows live in tensor memory)
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
             const int lrow = rev ? l0 - r : l0 + r;
-            al[r] = (lrow >= th.la && lrow < th.lb) ? ld4(a.alpha + (size_t)b * g.level + (size_t)(r0 + lrow) * pitch + th.x) : zero4;
+            const float4 av = (lrow >= th.la && lrow < th.lb) ? ld4(a.alpha + (size_t)b * g.level + (size_t)(r0 + lrow) * pitch + th.x) : zero4;
+            if (r < RMAX - ATM) al[r] = av;
+            else tm_st4(tm + 8 * RMAX + 4 * (r - (RMAX - ATM)), av.x, av.y, av.z, av.w);
         }
+        if (IMG && ATM > 0) tm_wait_st();
         float kapx[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -280,7 +354,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
         int src_mask = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) src_mask |= (th.src_lr >= 0 && xc[j] == xs) ? (1 << j) : 0;
-        const float bsrc = ADJ ? 0.0f : a.beta_src[gshot];
+        const float bsrc = (ADJ && !IMG) ? 0.0f : a.beta_src[gshot];
+        const float *ph_shot = IMG ? a.phist + (size_t)shot * hist_shot : nullptr;  // forward history of this shot (MODE 2)
         // adjoint mode: alpha of the receiver-row cells, lane of the (non-image) source cell, beta_dt accumulator
         float4 al_rec = zero4;
         int src_lane = -1;
@@ -303,6 +378,12 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
             float *dst = s_raw + buf * g.nrec;
             for (int r = lane_id; r < g.nrec; r += 32)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + r)), "l"(gt + r) : "memory");
+            if (IMG) {  // the receiver row of the forward level the cotangent row pairs with
+                const float *gp = ph_shot + (size_t)tr * g.level + (size_t)g.igz * pitch;
+                float *pd = s_prow + buf * pitch;
+                for (int c = lane_id; c < g.q4; c += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(pd + 4 * c)), "l"(gp + 4 * c) : "memory");
+            }
         };
         auto sum_cot = [&](const int tr, const int buf) {
             asm volatile("cp.async.wait_all;" ::: "memory");
@@ -315,13 +396,19 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                 float acc = 0.0f;
                 for (int k = s_rec_ptr[xx]; k < s_rec_ptr[xx + 1]; ++k) acc += raw[s_rec_idx[k]];
                 dst[xx] = acc;
+                if (IMG) s_ginj[xx] += acc * s_prow[buf * pitch + xx];
             }
         };
         if (ADJ && tid >= NT - 32 && has_rec_row) {  // level 0 of the loop is reverse time nt-1
+            if (IMG)
+                for (int xx = lane_id; xx < pitch; xx += 32) s_ginj[xx] = 0.0f;
             fetch_cot(a.nt - 1, 0);
             sum_cot(a.nt - 1, 0);
             fetch_cot(a.nt - 2, 1);
         }
+        if (IMG && tid == 0)
+            for (int d = 0; d < kImgPrefetchLevels && d < a.nt; ++d)
+                l2_prefetch_bulk(ph_shot + (size_t)(a.nt - 1 - d) * g.level + (size_t)r0 * pitch, (uint32_t)(nrows * pitch * sizeof(float)));
         __syncthreads();
         cluster_sync_all();  // shot boundary: every CTA has finished the previous shot and cleared its buffers
 
@@ -362,10 +449,16 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                 sum_cot(trev - 1, (t + 1) & 1);
                 fetch_cot(trev - 2, t & 1);
             }
+            if (IMG && tid == 0 && trev >= kImgPrefetchLevels)  // pull the slab of the forward level three sweeps ahead into L2
+                l2_prefetch_bulk(ph_shot + (size_t)(trev - kImgPrefetchLevels) * g.level + (size_t)r0 * pitch, (uint32_t)(nrows * pitch * sizeof(float)));
             if (warp_active) {
                 const uint64_t *push_bar = bars + 2 * pbuf + hp.bar;  // barrier of the buffer written now, at the receiver
-                if (rev) fwd_sweep<RMAX, PITCH, -1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
-                else fwd_sweep<RMAX, PITCH, 1, !ADJ>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends);
+                ImgThread im;
+                im.pg = IMG ? ph_shot + (size_t)trev * g.level + (size_t)(r0 + l0) * pitch + th.x : nullptr;
+                im.tm = tm;
+                im.ring = s_ring + tid * 4;
+                if (rev) fwd_sweep<RMAX, PITCH, -1, !ADJ, IMG, ATM>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends, im);
+                else fwd_sweep<RMAX, PITCH, 1, !ADJ, IMG, ATM>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends, im);
                 stamp(t, 2);
                 jitter<PERT>(a.perturb, 2, (unsigned)t);
                 if (ADJ) {
@@ -424,21 +517,57 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                            smem + prv + 2 * pitch, (uint32_t)(nrows * pitch * sizeof(float)));
         };
         for (int t = 0, cur = 0; t < a.nt; ++t, cur = slab - cur) level(t, cur, slab - cur);
+        float gb_over_al = 0.0f;
         if (ADJ && src_lane >= 0) {
             const float4 alv = ld4(a.alpha + (size_t)b * g.level + (size_t)(r0 + th.src_lr) * pitch + th.x);
-            a.Gb[gshot] = gb / (src_lane == 0 ? alv.x : src_lane == 1 ? alv.y : src_lane == 2 ? alv.z : alv.w);
+            gb_over_al = gb / (src_lane == 0 ? alv.x : src_lane == 1 ? alv.y : src_lane == 2 ? alv.z : alv.w);
+            a.Gb[gshot] = gb_over_al;
         }
         if (a.hist != nullptr && tid == 0) bulk_wait_read();
+        __syncthreads();
+        if (IMG && warp_active) {
+            // imaging planes of this shot (what k_imaging writes): Ga = sums / alpha^2, Gk = sums / alpha; the accumulators go
+            // back to zero for the cluster's next shot
+            const int nvalid = th.lb - th.la;
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                float ga[4], gk[4];
+                tm_ld4(tm + 4 * r, ga);
+                tm_ld4(tm + 4 * RMAX + 4 * r, gk);
+                tm_wait_ld(ga, gk);
+                tm_st4(tm + 4 * r, 0.f, 0.f, 0.f, 0.f);
+                tm_st4(tm + 4 * RMAX + 4 * r, 0.f, 0.f, 0.f, 0.f);
+                if (r < nvalid) {
+                    const int lrow = rev ? l0 - r : l0 + r;
+                    const size_t off = (size_t)(r0 + lrow) * pitch + th.x;
+                    const float4 av = ld4(a.alpha + (size_t)b * g.level + off);
+                    const float a4[4] = {av.x, av.y, av.z, av.w};
+                    if (lrow == th.rec_lr) {  // the injected cotangent's share: alpha * sum_t p_t g_t
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ga[j] += a4[j] * s_ginj[xc[j]];
+                    }
+                    if (lrow == th.src_lr && src_lane >= 0) {  // the forward recurrence had the extra term beta_src w_t at the source cell
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j == src_lane) ga[j] -= bsrc * (gb_over_al * a4[j]);
+                    }
+                    st4(a.Ga + (size_t)gshot * g.level + off, make_float4(ga[0] / (a4[0] * a4[0]), ga[1] / (a4[1] * a4[1]), ga[2] / (a4[2] * a4[2]), ga[3] / (a4[3] * a4[3])));
+                    st4(a.Gk + (size_t)gshot * g.level + off, make_float4(gk[0] / a4[0], gk[1] / a4[1], gk[2] / a4[2], gk[3] / a4[3]));
+                }
+            }
+            tm_wait_st();
+        }
         __syncthreads();
     }
     if (tid == 0) bulk_wait_all();
     cluster_sync_all();  // no CTA exits while a neighbour may still address its shared memory
+    if (IMG && tid < 32) tm_free_all(s_tmem);
 }
 
 }  // namespace
 
 // Smallest cluster (1..8 CTAs, or the non-portable 16) whose slabs fit when every thread marches R rows.
-static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, ClusterConfig *cfg)
+static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, ClusterConfig *cfg, const bool img)
 {
     const Grid &g = p.g;
     const int nthreads = kClusterThreads;
@@ -457,11 +586,13 @@ static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, 
         const int ngroups = (maxrows + R - 1) / R;  // each thread marches R rows
         if (ngroups > groups_max) continue;
         const int slabrows = ngroups * R;  // >= maxrows: rows past the slab are computed but never stored
-        size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + g.nxp + 1 + g.nrec + 2 * g.nxp + 2 * g.nrec) * sizeof(float);
+        size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + 3 * g.pitch + g.nxp + 1 + g.nrec + 2 * g.nxp + 2 * g.nrec) * sizeof(float);
+        if (img) smem += 2 * kClusterThreads * 16 + 16;  // resident imaging: two 16-byte slots per thread for the forward rows
         if (smem > (size_t)max_smem) continue;
         const size_t room = (size_t)max_smem;
-        cfg->wav_smem = smem + (size_t)p.nt * sizeof(float) <= room;
+        cfg->wav_smem = !img && smem + (size_t)p.nt * sizeof(float) <= room;
         if (cfg->wav_smem) smem += (size_t)p.nt * sizeof(float);
+        cfg->img = img;
         cfg->nthreads = nthreads;
         cfg->C = C; cfg->maxrows = maxrows; cfg->ngroups = ngroups; cfg->slabrows = slabrows; cfg->smem = smem;
         cfg->rmax = R;
@@ -470,10 +601,10 @@ static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, 
     return false;
 }
 
-bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots)
+bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots, bool img)
 {
-    if (p.cluster_rows > 0) return cluster_config_rows(p, p.cluster_rows, true, cfg);  // forced (tests, tuning)
-    if (!cluster_config_rows(p, kClusterRowsMax, false, cfg)) return false;
+    if (p.cluster_rows > 0) return cluster_config_rows(p, p.cluster_rows, true, cfg, img);  // forced (tests, tuning)
+    if (!cluster_config_rows(p, kClusterRowsMax, false, cfg, img)) return false;
     if (nshots <= 0 || p.cluster_size != 0) return true;
     // Few shots (one model of the reference's configs has 5): the throughput configuration would occupy nshots * C of
     // the 148 SMs and every level would still cost a full 13-row sweep.  A level is latency-bound (one shot's level takes
@@ -483,17 +614,17 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots)
     static const int kWideRows[2] = {4, 7};
     for (int i = 0; i < 2; ++i) {
         ClusterConfig wide;
-        if (!cluster_config_rows(p, kWideRows[i], true, &wide) || wide.C <= cfg->C) continue;
+        if (!cluster_config_rows(p, kWideRows[i], true, &wide, img) || wide.C <= cfg->C) continue;
         if (fwd_cluster_wave(p, wide) >= nshots) { *cfg = wide; return true; }
     }
     return true;
 }
 
-template <int R, int PITCH, bool ADJ, bool PERT>
+template <int R, int PITCH, int MODE, bool PERT>
 static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st, int *wave_only)
 {
     constexpr int NT = kClusterThreads;
-    auto kernel = k_fwd_cluster<R, PITCH, ADJ, PERT>;
+    auto kernel = k_fwd_cluster<R, PITCH, MODE, PERT>;
     a.slabrows = cc.slabrows; a.ngroups = cc.ngroups; a.wav_smem = cc.wav_smem ? 1 : 0;
 
     cudaLaunchConfig_t cfg{};
@@ -548,10 +679,15 @@ static cudaError_t launch_fwd_cluster_t(const Plan &p, const ClusterConfig &cc, 
 template <int R, int PITCH>
 static cudaError_t dispatch_fwd_cluster_rp(const Plan &p, const ClusterConfig &cc, const ClusterFwdArgs &a, cudaStream_t st, int *wave_only)
 {
-    const bool adj = a.adj_mode != 0;
+#ifndef RDFWI_DEV_FAST  // (development builds compile the production instantiations only)
     if (a.perturb != 0)  // debug instantiations (schedule perturbation)
-        return adj ? launch_fwd_cluster_t<R, PITCH, true, true>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, PITCH, false, true>(p, cc, a, st, wave_only);
-    return adj ? launch_fwd_cluster_t<R, PITCH, true, false>(p, cc, a, st, wave_only) : launch_fwd_cluster_t<R, PITCH, false, false>(p, cc, a, st, wave_only);
+        return a.adj_mode == 2   ? launch_fwd_cluster_t<R, PITCH, 2, true>(p, cc, a, st, wave_only)
+               : a.adj_mode == 1 ? launch_fwd_cluster_t<R, PITCH, 1, true>(p, cc, a, st, wave_only)
+                                 : launch_fwd_cluster_t<R, PITCH, 0, true>(p, cc, a, st, wave_only);
+#endif
+    return a.adj_mode == 2   ? launch_fwd_cluster_t<R, PITCH, 2, false>(p, cc, a, st, wave_only)
+           : a.adj_mode == 1 ? launch_fwd_cluster_t<R, PITCH, 1, false>(p, cc, a, st, wave_only)
+                             : launch_fwd_cluster_t<R, PITCH, 0, false>(p, cc, a, st, wave_only);
 }
 
 template <int R>
@@ -561,8 +697,12 @@ static cudaError_t dispatch_fwd_cluster_r(const Plan &p, const ClusterConfig &cc
     // x-neighbour PAIRS from shared memory, which needs an even padded width
     switch ((p.g.nxp & 1) == 0 ? p.g.pitch : 0) {
         case 312: return dispatch_fwd_cluster_rp<R, 312>(p, cc, a, st, wave_only);
+#ifndef RDFWI_DEV_FAST
         case 432: return dispatch_fwd_cluster_rp<R, 432>(p, cc, a, st, wave_only);
         default: return dispatch_fwd_cluster_rp<R, 0>(p, cc, a, st, wave_only);
+#else
+        default: return cudaErrorInvalidValue;
+#endif
     }
 }
 
@@ -570,8 +710,10 @@ static cudaError_t dispatch_fwd_cluster(const Plan &p, const ClusterConfig &cc, 
 {
     switch (cc.rmax) {  // rows marched per thread: 13 for throughput, 7 / 4 on wider clusters when the shots are few
         case kClusterRowsMax: return dispatch_fwd_cluster_r<kClusterRowsMax>(p, cc, a, st, wave_only);
+#ifndef RDFWI_DEV_FAST
         case 7: return dispatch_fwd_cluster_r<7>(p, cc, a, st, wave_only);
         case 4: return dispatch_fwd_cluster_r<4>(p, cc, a, st, wave_only);
+#endif
         default: return cudaErrorInvalidValue;
     }
 }
@@ -589,11 +731,11 @@ cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFw
 // SMs / C when the occupancy query is not available (no device).
 int fwd_cluster_wave(const Plan &p, const ClusterConfig &cc)
 {
-    const int key = (cc.C * 64 + cc.rmax) * 1024 + cc.nthreads;
+    const int key = ((cc.C * 64 + cc.rmax) * 1024 + cc.nthreads) * 2 + (cc.img ? 1 : 0);
     for (int i = 0; i < p.wave_n; ++i)
         if (p.wave_keys[i] == key) return p.wave_vals[i];
     ClusterFwdArgs a{};
-    a.adj_mode = 1;
+    a.adj_mode = cc.img ? 2 : 1;
     int wave = 0;
     if (dispatch_fwd_cluster(p, cc, a, nullptr, &wave) != cudaSuccess || wave < 1) {
         cudaGetLastError();

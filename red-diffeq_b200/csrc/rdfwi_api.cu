@@ -341,6 +341,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "engine") { if (value < 0 || value > 2) goto bad; p->engine = (int)value; }
     else if (k == "history_segment") { if (value < 0 || value == 1 || value == 2) goto bad; p->history_segment = (int)value; }
     else if (k == "adj_mode") { if (value < 0 || value > 1) goto bad; p->adj_mode = (int)value; }
+    else if (k == "imaging") { if (value < 0 || value > 2) goto bad; p->imaging = (int)value; }
     else if (k == "timing") { clear_spans(p); p->timing = value != 0; }  // (re)starts the per-kernel-class timers
     else if (k == "u_chunk_shots") { if (value < 0) goto bad; p->u_chunk_shots = (int)value; }
     else if (k == "scratch_mb") { if (value < 0) goto bad; p->scratch_mb = value; }
@@ -367,10 +368,11 @@ int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *out)
     else if (k == "engine") *out = p->engine;
     else if (k == "history_segment") *out = p->history_segment;
     else if (k == "adj_mode") *out = p->adj_mode;
+    else if (k == "imaging") *out = p->imaging;
     else if (k.rfind("us_", 0) == 0 || k.rfind("n_", 0) == 0) {
         const bool want_us = k[0] == 'u';
         const std::string what = k.substr(want_us ? 3 : 2);
-        const int kind = what == "forward" ? 0 : what == "adjoint_field" ? 1 : what == "imaging" ? 2 : what == "adjoint_loop" ? 3 : -1;
+        const int kind = what == "forward" ? 0 : what == "adjoint_field" ? 1 : what == "imaging" ? 2 : what == "adjoint_loop" ? 3 : what == "adjoint_resident" ? 4 : -1;
         if (kind < 0) { set_error("unknown timer " + k); return RDFWI_EINVAL; }
         double us; int n;
         span_total(p, kind, &us, &n);
@@ -531,6 +533,34 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     ClusterConfig cc;
     const_cast<Plan &>(p).last_split = (!ckpt && w.split) ? (w.recompute ? 2 : 1) : 0;
     const_cast<Plan &>(p).last_u_chunk = w.u_chunk;
+    if (!ckpt && w.split && p.imaging != 1 && cluster_config(p, &cc, w.recompute ? std::min(w.u_chunk, B * g.ns) : B * g.ns, true)) {
+        // resident imaging: ONE cluster-resident kernel per launch runs the adjoint field and forms the imaging sums in the
+        // sweep (accumulators in tensor memory), reading the forward history once; no adjoint-field history, no imaging pass
+        const int nshots = B * g.ns;
+        const int step = w.recompute ? w.u_chunk : nshots;
+        const_cast<Plan &>(p).last_split = w.recompute ? 5 : 4;
+        for (int s0 = 0; s0 < nshots; s0 += step) {
+            const int n = std::min(step, nshots - s0);
+            ClusterFwdArgs a{};
+            a.alpha = w.alpha; a.kap = w.kap; a.beta_src = w.beta_src;
+            a.isx = p.d_isx; a.rec_ptr = p.d_rec_ptr; a.rec_idx = p.d_rec_idx; a.wavelet = p.d_wavelet;
+            a.nshots = n; a.nt = nt; a.st = p.st; a.shot0 = s0; a.trace = p.trace_ptr;
+            if (w.recompute) {  // forward field of the chunk, again, this time keeping every level (no seismograms)
+                ClusterConfig fcc;
+                if (!cluster_config(p, &fcc, n)) { set_error("no cluster configuration for the recomputed forward field"); return RDFWI_EINVAL; }
+                a.seis = nullptr; a.hist = w.p_hist; a.adj_mode = 0;
+                Timed timed(p, 0, st);
+                RD_CUDA(launch_fwd_cluster(p, fcc, a, st));
+            }
+            a.seis = nullptr; a.hist = nullptr; a.adj_mode = 2; a.cot = cot; a.Gb = w.Gb;
+            a.phist = w.recompute ? w.p_hist : hist + (size_t)s0 * nt * g.level;
+            a.Ga = w.Ga; a.Gk = w.Gk;
+            Timed timed(p, 4, st);
+            RD_CUDA(launch_fwd_cluster(p, cc, a, st));
+        }
+        RD_CUDA(launch_gradient_epilogue(p, v, B, w.Ga, w.Gk, w.Gb, w.g_planes, w.argmin, w.fold_tmp, w.vel_part, grad_v, st));
+        return RDFWI_OK;
+    }
     if (!ckpt && w.split && cluster_config(p, &cc, std::min(w.u_chunk, B * g.ns))) {
         // split adjoint: per chunk of shots, (1) the cluster-resident kernel runs the adjoint field in the u-variable
         // and streams it to HBM, (2) a streaming kernel forms the imaging sums from the two histories

@@ -62,6 +62,8 @@ struct Plan {
     int cluster_size = 0;   // 0 = smallest cluster that fits
     int cluster_rows = 0;   // rows marched per thread of k_fwd_cluster: 0 = auto (13; 7 or 4 on wider clusters for few shots)
     int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused per-level adjoint (k_adj_step)
+    int imaging = 1;          // cluster engine: where the imaging sums are formed -- 1 = streaming kernel over two histories
+                              // (split adjoint), 2 = inside the adjoint sweep, accumulators in tensor memory; 0 = auto
     int perturb = 0;          // debug: seed of the schedule perturbation of k_fwd_cluster (0 = off), see rdfwi.h
     int img_prefetch = 0;     // imaging kernel: levels ahead pulled into L2 (0 = default 4)
     long long *trace_ptr = nullptr;  // debug: device buffer for per-warp timeline stamps of k_fwd_cluster
@@ -71,7 +73,8 @@ struct Plan {
     // optional per-kernel-class timing with CUDA events on the caller's stream (rdfwi_plan_set "timing")
     int timing = 0;
     struct Span { cudaEvent_t a, b; int kind; };
-    std::vector<Span> spans;  // kind: 0 forward time loop, 1 adjoint-field time loop, 2 imaging, 3 fused / per-level adjoint loop
+    std::vector<Span> spans;  // kind: 0 forward time loop, 1 adjoint-field time loop, 2 imaging, 3 fused / per-level adjoint loop,
+                              // 4 cluster-resident adjoint with the imaging sums in the sweep
     int history_segment = 0;  // 0 = keep every level; K >= 3 = checkpoint pairs every K levels, recompute in the backward pass
                               // (K >= nt: no history at all -- the backward pass recomputes the forward field chunk by chunk)
     long long scratch_mb = 0; // cap on ONE scratch history of the split adjoint, MB (0 = 40000)
@@ -93,7 +96,10 @@ struct ClusterFwdArgs {
     int nshots, nt, st;
     long long *trace;       // debug: per-warp clock64 stamps (nullptr = off)
     int shot0;              // global index of the launch's first shot (seis / cot / Gb / model lookup)
-    int adj_mode;           // 0 = forward wavefield, 1 = adjoint field in the u-variable (see k_fwd_cluster)
+    int adj_mode;           // 0 = forward wavefield, 1 = adjoint field in the u-variable -> hist, 2 = adjoint field with the
+                            // imaging sums formed in the kernel (accumulators in tensor memory) -> Ga, Gk (see k_fwd_cluster)
+    const float *phist;     // mode 2: forward history [shot][t][z][x] of the launch's shots (launch-local shot index)
+    float *Ga, *Gk;         // mode 2: (B*ns, nzp, pitch) imaging planes per shot
     const float *cot;       // adjoint mode: (B*ns, nt_out, nrec) cotangent of the seismograms
     float *Gb;              // adjoint mode: (B*ns) sum_t u_t[src] w_t / alpha_src
     int slabrows, ngroups, wav_smem;  // filled by launch_fwd_cluster from the ClusterConfig
@@ -108,6 +114,7 @@ struct ClusterConfig {
     size_t smem = 0;  // dynamic shared memory per CTA
     int rmax = 0;     // rows per thread (template instantiation)
     bool wav_smem = false;  // the wavelet is staged in shared memory
+    bool img = false;       // sized for the resident imaging (MODE 2 of k_fwd_cluster: two 16-byte slots per thread more)
     int nthreads = 512;     // threads per CTA
 };
 
@@ -181,7 +188,7 @@ int adj_shot_slices(const Plan &p, int nb);  // imaging planes per model the per
 // nshots = 0: the throughput configuration (smallest cluster that fits, 13 rows per thread).  nshots > 0: the
 // configuration for a launch of that many shots -- when they are so few that they leave most SMs idle, a wider cluster
 // with fewer rows per thread (shorter sweeps, same arithmetic per cell) as long as all shots stay co-resident.
-bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots = 0);
+bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots = 0, bool img = false);
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st);
 int fwd_cluster_wave(const Plan &p, const ClusterConfig &cc);  // co-resident clusters = shots in flight per wave
 // kernels_imaging.cu: zero-lag imaging sums of `nshots` shots from the forward history and the adjoint-field history

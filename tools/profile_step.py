@@ -17,7 +17,7 @@ nt = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 ctx = dict(synthetic.PDE_OPENFWI)
 ctx["nt"] = nt
 op = FWIForward(ctx, "cuda:0", normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
-for kv in sys.argv[3:]:
+for kv in [a for a in sys.argv[3:] if "=" in a]:
     k, v = kv.split("=")
     op.set_option(k, int(v))
 v = torch.tensor(synthetic.velocity_models(B, 70, 70), device="cuda:0", requires_grad=True)
