@@ -95,7 +95,8 @@ def classify_kernel(name):
     """Kernel class of a demangled kernel name as ncu prints it (None = not one of the time-loop kernels)."""
     if "k_fwd_cluster<" in name:
         targs = name.split("k_fwd_cluster<", 1)[1].split(">", 1)[0].replace(" ", "").split(",")
-        return "adjoint_field" if targs[2] in ("true", "(bool)1", "1") else "forward"
+        mode = targs[2].replace("(int)", "").replace("(bool)", "")
+        return "adjoint_resident" if mode == "2" else ("adjoint_field" if mode in ("true", "1") else "forward")
     if "k_step_tile<" in name:
         targs = name.split("k_step_tile<", 1)[1].split(">", 1)[0].replace(" ", "").split(",")
         return "adjoint_field" if targs[-1] in ("true", "(bool)1", "1") else "forward"
@@ -426,7 +427,7 @@ def measure_workload(env, workload, steps, warmup, opts=(), history_segment=None
     t_stop.record()
     env.barrier()
     elapsed_ms = t_start.elapsed_time(t_stop)
-    classes = ("forward", "adjoint_field", "imaging", "adjoint_loop")
+    classes = ("forward", "adjoint_field", "imaging", "adjoint_loop", "adjoint_resident")
     kernel_us = {k: plan.get("us_" + k) for k in classes}
     kernel_n = {k: plan.get("n_" + k) for k in classes}
     plan.set("timing", 0)
@@ -492,7 +493,8 @@ def roofline_block(m, steps):
     peak, peak_src = measured_peak_gbs()
     p = m["plan"]
     nt = m["nt"]
-    recompute = p["adj_split"] == 2      # no history kept: the backward pass re-runs the forward kernel per chunk
+    recompute = p["adj_split"] in (2, 5)  # no history kept: the backward pass re-runs the forward kernel per chunk
+    resident = p["adj_split"] in (4, 5)   # cluster engine, imaging sums formed inside the adjoint sweep (tensor memory)
     fwd_cluster = m["engine_opt"] != 1 and p["cluster_size_used"] > 0 and (m["segment"] == 0 or recompute)
     adj_split = p["adj_split"] >= 1
     us, n = m["kernel_us"], m["kernel_n"]
@@ -503,7 +505,11 @@ def roofline_block(m, steps):
                     # recompute tier: the forward kernel really runs twice per step (modelling + per-chunk recompute)
                     "algo_bytes": ALGO_BYTES_FWD * cell_updates * (2 if recompute else 1)},
     }
-    if adj_split:
+    if resident:
+        # one kernel: adjoint field on chip, forward history read once, imaging accumulators in tensor memory
+        kernels["adjoint_resident"] = {"kernel": "k_fwd_cluster<ADJ+IMAGING>", "us": us["adjoint_resident"], "launches": n["adjoint_resident"],
+                                       "algo_bytes": ALGO_BYTES_ADJ * cell_updates}
+    elif adj_split:
         # the adjoint's 16 B / cell-update split as: adjoint-field kernel (read u_{t+1}, u_{t+2}, write u_t = 12 B; all of
         # it stays in shared memory, only the 4 B history write reaches HBM) + imaging kernel (pointwise: read p_t and
         # u_t once each = 8 B, which is exactly what it streams from HBM)
@@ -578,12 +584,14 @@ def roofline_block(m, steps):
 
 def config_block(m):
     p = m["plan"]
-    recompute = p["adj_split"] == 2
+    recompute = p["adj_split"] in (2, 5)
     fwd_cluster = m["engine_opt"] != 1 and p["cluster_size_used"] > 0 and (m["segment"] == 0 or recompute)
     adj_split = p["adj_split"] >= 1
     seg = m["segment"]
     adj_txt = "per-level fused"
-    if adj_split:
+    if p["adj_split"] in (4, 5):
+        adj_txt = "cluster-resident adjoint field with the imaging sums formed in the sweep (accumulators in tensor memory; C=%d)" % p["cluster_size_last"]
+    elif adj_split:
         adj_txt = ("split: per-level tiled adjoint field + streaming imaging" if p["adj_split"] == 3 else
                    "split: cluster-resident adjoint field (C=%d) + streaming imaging" % p["cluster_size_last"])
     return {"workload": m["workload"], "models_per_gpu": m["B"], "shots_per_model": m["ns"], "shots_on_rank0": m["ns_local"],

@@ -64,8 +64,11 @@ int rdfwi_plan_destroy(rdfwi_plan plan);
 
 /* Tunables (all optional).  Keys:
  *   "engine"         0 = by problem size (default), 1 = per-level tiled kernels, 2 = cluster-resident time loop
- *   "adj_mode"       0 = split adjoint (adjoint-field kernel + streaming imaging kernel; default), 1 = fused per-level
- *                    adjoint (one launch per level, imaging sums read-modify-written in HBM; needs no scratch history)
+ *   "adj_mode"       0 = adjoint on the engine the forward pass ran on (default), 1 = fused per-level adjoint (one launch
+ *                    per level, imaging sums read-modify-written in HBM; needs no scratch history)
+ *   "imaging"        cluster-resident engine: where the zero-lag imaging sums are formed.  0 / 2 = inside the adjoint sweep,
+ *                    accumulators in tensor memory, forward history read once (default); 1 = split adjoint: the adjoint
+ *                    field is written to a scratch history and a streaming kernel reads both histories
  *   "history_segment" 0 = keep every level; K >= 3 = keep a pair of levels every K levels and recompute K levels at a
  *                    time in the backward pass; K >= nt = keep nothing, the backward pass recomputes the forward field
  *                    chunk by chunk (must be set BEFORE the workspace / history sizes are queried; the `segment`
@@ -78,7 +81,7 @@ int rdfwi_plan_destroy(rdfwi_plan plan);
  *   "rows_per_thread" (1, 2, 4, 8; tile rows = 8x) / "adj_rows_per_thread"  z-rows marched per thread, per-level kernels
  *   "chunk_models"   models advanced together by the per-level forward (0 = auto)
  *   "timing"         1 = record CUDA events around each kernel class on the caller's stream (read back as "us_<class>",
- *                    "n_<class>" with class in forward, adjoint_field, imaging, adjoint_loop).  EXCEPTION to "the library
+ *                    "n_<class>" with class in forward, adjoint_field, imaging, adjoint_loop, adjoint_resident).  EXCEPTION to "the library
  *                    never synchronises": rdfwi_plan_get("us_*" / "n_*") waits (cudaEventSynchronize) for the recorded
  *                    events, i.e. for the timed work -- a measurement hook, never called by forward / backward themselves
  *   "perturb"        debug: seed (> 0) of pseudo-random per-warp delays (up to ~4 us) in front of every synchronisation point

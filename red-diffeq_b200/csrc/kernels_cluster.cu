@@ -49,7 +49,10 @@ namespace {
 // (65 ms per 64 models, 40 ms with the loads removed: profiles/resident_adjoint_r2.md).  So each thread owns two 16-byte
 // slots in shared memory and fills them with cp.async two rows ahead: asynchronous, no registers, no scheduler to argue
 // with; the slab of the level three sweeps ahead is pulled into L2 by one bulk prefetch per level.
-constexpr int kImgPrefetchLevels = 3;
+#ifndef RDFWI_IMG_PF
+#define RDFWI_IMG_PF 3
+#endif
+constexpr int kImgPrefetchLevels = RDFWI_IMG_PF;
 template <int RMAX, int PITCH, int DIR, bool EXACT, bool IMG, int ATM>
 __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cur, const int prv, const int kap_off,
                                           const int pitch_rt, const int l0, const SweepThread &th,
@@ -68,9 +71,10 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
     const int nvalid = th.lb - th.la;
     // forward-history rows of the thread, two in flight (rows the thread does not own re-read its first row: in bounds)
     const uint32_t ring0 = IMG ? smem_u32(im.ring) : 0, ring1 = ring0 + kClusterThreads * 16;
-    if (IMG) {  // rows the thread does not own re-read its first row (in bounds); their sums are never written out
+    if (IMG) {  // rows the thread does not own are fetched all the same (immediate offsets: no address arithmetic per row);
+                // they lie inside the history or the kClusterRowsMax rows of padding behind it, their sums are never written out
         cp_async16_commit(ring0, im.pg);
-        cp_async16_commit(ring1, im.pg + (1 < nvalid ? P : 0));
+        cp_async16_commit(ring1, im.pg + P);
     }
 
     float4 w0 = ld4(cb - 2 * P), w1 = ld4(cb - P), w2 = ld4(cb), w3 = ld4(cb + P);
@@ -86,7 +90,7 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             if (r + 1 < RMAX) cp_async_wait<1>();  // this row's copy has landed (the next row's may be in flight)
             else cp_async_wait<0>();
             pv = lds4_volatile(slot);
-            if (r + 2 < RMAX) cp_async16_commit(slot, im.pg + (r + 2 < nvalid ? (r + 2) * P : 0));
+            if (r + 2 < RMAX) cp_async16_commit(slot, im.pg + (r + 2) * P);
         }
         const float4 w4 = ld4(cb + (r + 2) * P);
         const float4 old = ld4(pb + r * P);
@@ -133,6 +137,7 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             const float2 s2 = f2add(f2add(f2add(up2, dn2), make_float2(e[j], e[j + 1])), make_float2(e[j + 4], e[j + 5]));
             // kappa = column profile in sponge columns, row profile elsewhere (get_Abc: columns override rows): selected
             // arithmetically -- 1 * kapz + 0 and 0 * kapz + kapx are exact -- so no predicate registers are tied up
+            // (adjoint modes: kapx holds 1 - kappa_col and th.mz is negated, so the same FMA gives 1 - kappa directly)
             const float2 kp = f2fma(make_float2(th.mz[j], th.mz[j + 1]), make_float2(kapz, kapz), make_float2(kapx[j], kapx[j + 1]));
             float2 res;
             if (EXACT) {  // forward wavefield: one rounding per reference op, products never packed (see above)
@@ -144,17 +149,21 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
                 const float2 a2 = make_float2(__fmul_rn(t2.x, oldp.x), __fmul_rn(t2.y, oldp.y));
                 const float2 a3 = make_float2(__fmul_rn(alp.x, lap.x), __fmul_rn(alp.y, lap.y));
                 res = f2add(f2sub(a1, a2), a3);
-            } else {      // adjoint field: no bit-parity requirement, packed FMA throughout
+            } else {
+                // adjoint field: no bit-parity requirement, so packed FMAs and the recurrence regrouped around
+                //     L = (4/3) s1 - (1/12) s2 - 5 u1,    d = u1 - u2,    u = alpha L + (u1 + (1 - kappa) d)
+                // (identical to (2 - 5 alpha - kappa) u1 - (1 - kappa) u2 + alpha lap: 8 instead of 10 packed operations).
+                // It also hands the imaging terms over for free: u - (2-kappa) u1 + (1-kappa) u2 = alpha L, u2 - u1 = -d.
                 const float2 cen = make_float2(e[j + 2], e[j + 3]);
-                const float2 lap = f2fma(make_float2(c2, c2), s1, f2mul(make_float2(c3, c3), s2));
-                const float2 t1 = f2sub(f2fma(make_float2(-5.0f, -5.0f), alp, make_float2(2.0f, 2.0f)), kp);
-                const float2 t2 = f2sub(make_float2(1.0f, 1.0f), kp);
-                res = f2fma(alp, lap, f2sub(f2mul(t1, cen), f2mul(t2, oldp)));
-                if (IMG) {  // same expression tree as k_imaging: p * ((u - (2-k) u1) + (1-k) u2), p * (u2 - u1)
+                const float2 t2 = kp;  // 1 - kappa (see above)
+                const float2 L = f2fma(make_float2(c2, c2), s1, f2fma(make_float2(c3, c3), s2, f2mul(cen, make_float2(-5.0f, -5.0f))));
+                const float2 d = f2sub(cen, oldp);
+                const float2 aL = f2mul(alp, L);
+                res = f2add(aL, f2fma(d, t2, cen));
+                if (IMG) {  // ga += p alpha L,  gk += p d  (the sign of gk is put right when the planes are written)
                     const float2 pp = h ? make_float2(pv.z, pv.w) : make_float2(pv.x, pv.y);
-                    const float2 br = f2fma(t2, oldp, f2fma(f2sub(kp, make_float2(2.0f, 2.0f)), cen, res));
-                    const float2 na = f2fma(pp, br, make_float2(ga[j], ga[j + 1]));
-                    const float2 nk = f2fma(pp, f2sub(oldp, cen), make_float2(gk[j], gk[j + 1]));
+                    const float2 na = f2fma(pp, aL, make_float2(ga[j], ga[j + 1]));
+                    const float2 nk = f2fma(pp, d, make_float2(gk[j], gk[j + 1]));
                     ga[j] = na.x; ga[j + 1] = na.y; gk[j] = nk.x; gk[j + 1] = nk.y;
                 }
             }
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     for (int j = 0; j < 4; ++j) {
         xc[j] = th.x + j >= g.nxp ? th.x + j - g.nxp : th.x + j;
         th.colsp[j] = sponge_index(xc[j], g.nxp, g.nbc) >= 0;
-        th.mz[j] = th.colsp[j] ? 0.0f : 1.0f;
+        th.mz[j] = th.colsp[j] ? 0.0f : (ADJ ? -1.0f : 1.0f);  // adjoint modes form 1 - kappa: (1 - kappa_col) - mz kappa_row
     }
     // rows this thread must handle in the epilogue (local row index, or -1)
     th.src_lr = (g.isz - r0 >= th.la && g.isz - r0 < th.lb) ? g.isz - r0 : -1;
@@ -349,6 +358,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
         for (int j = 0; j < 4; ++j) {
             const int kx = sponge_index(xc[j], g.nxp, g.nbc);
             kapx[j] = kx >= 0 ? kap_b[kx] : 0.0f;
+            if (ADJ) kapx[j] = 1.0f - kapx[j];
         }
         const int xs = a.isx[s];
         int src_mask = 0;
@@ -552,7 +562,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                             if (j == src_lane) ga[j] -= bsrc * (gb_over_al * a4[j]);
                     }
                     st4(a.Ga + (size_t)gshot * g.level + off, make_float4(ga[0] / (a4[0] * a4[0]), ga[1] / (a4[1] * a4[1]), ga[2] / (a4[2] * a4[2]), ga[3] / (a4[3] * a4[3])));
-                    st4(a.Gk + (size_t)gshot * g.level + off, make_float4(gk[0] / a4[0], gk[1] / a4[1], gk[2] / a4[2], gk[3] / a4[3]));
+                    st4(a.Gk + (size_t)gshot * g.level + off, make_float4(-gk[0] / a4[0], -gk[1] / a4[1], -gk[2] / a4[2], -gk[3] / a4[3]));
                 }
             }
             tm_wait_st();

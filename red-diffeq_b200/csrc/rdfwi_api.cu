@@ -113,6 +113,7 @@ struct Workspace {
     bool split = false;
     bool split_tile = false;  // split adjoint on the per-level engine: tiled adjoint-field levels + streaming imaging
     bool recompute = false;   // split adjoint on a forward history recomputed chunk by chunk (history_segment >= nt)
+    bool resident = false;    // cluster engine, imaging sums formed inside the adjoint sweep (tensor memory): no adjoint-field history
     int u_chunk = 0;
     float *u_hist = nullptr;
     float *p_hist = nullptr;  // recompute mode: forward history of one chunk of shots
@@ -149,16 +150,19 @@ Workspace carve(const Plan &p, int B, void *base)
     const bool cluster_ok = p.engine != 1 && (p.history_segment == 0 || single_segment);
     w.split = cluster_ok && (p.adj_mode == 0 || single_segment) && cluster_config(p, &fcc);
     w.recompute = w.split && single_segment;
+    ClusterConfig icc;  // the same with room for the resident imaging's staging slots (may need a larger cluster)
+    w.resident = w.split && p.imaging != 1 && cluster_config(p, &icc, 0, true);
     w.u_chunk = 0;
     if (w.split) {
         // Shots whose adjoint-field history is in flight at once: whole waves of co-resident clusters (33 four-CTA or 24
         // six-CTA clusters per wave), two waves when the scratch cap allows, evened out over the chunks (long records that
         // leave less than a wave per chunk are better served by history_segment >= nt: the operator's policy picks that).
         const int nshots = B * g.ns;
-        const int wave = cached_wave(p, fcc);
+        const int wave = cached_wave(p, w.resident ? icc : fcc);
         const double per_shot = (double)p.nt * (double)g.level * sizeof(float);
         // cap on one scratch history: 40 GB beside a full forward history, 55 GB each for the two of the recompute tier
-        const double cap = p.scratch_mb > 0 ? 1e6 * (double)p.scratch_mb : (single_segment ? 55e9 : 40e9);
+        // (resident imaging needs no adjoint-field history: the recompute tier's one scratch history may take 110 GB)
+        const double cap = p.scratch_mb > 0 ? 1e6 * (double)p.scratch_mb : (single_segment ? (w.resident ? 110e9 : 55e9) : 40e9);
         int chunk = p.u_chunk_shots;
         if (chunk <= 0) {
             const int fit = std::max(1, (int)(cap / per_shot));
@@ -190,8 +194,8 @@ Workspace carve(const Plan &p, int B, void *base)
     // checkpoint mode: the levels of one segment of one chunk, recomputed during the backward pass
     w.seg_hist = (p.history_segment > 0 && !w.recompute) ? (float *)take(w.chunk_level * (size_t)(p.history_segment - 1) * 4) : nullptr;
     // split adjoint: adjoint-field history of one chunk of shots (+ the recomputed forward history of the chunk)
-    if (w.split || w.split_tile) w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
-    if (w.recompute) w.p_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
+    if ((w.split && !w.resident) || w.split_tile) w.u_hist = (float *)take((size_t)w.u_chunk * (size_t)p.nt * g.level * 4);
+    if (w.recompute) w.p_hist = (float *)take(((size_t)w.u_chunk * (size_t)p.nt * g.level + (size_t)kClusterRowsMax * g.pitch) * 4);
     w.bytes = off;
     return w;
 }
@@ -217,7 +221,9 @@ size_t history_floats(const Plan &p, int B, int segment)
 {
     if (segment > 0)  // the pair (p_{jK-2}, p_{jK-1}) in front of every segment j >= 1
         return (size_t)B * p.g.ns * (size_t)std::max(num_segments(p, segment) - 1, 0) * 2 * p.g.level;
-    return (size_t)B * p.g.ns * (size_t)p.nt * p.g.level;  // every level p_0 .. p_{nt-1}
+    // every level p_0 .. p_{nt-1}, and a few rows of padding: the resident adjoint's sweeps fetch whole 13-row columns of a
+    // slab, the last of which may reach past the last level of the last shot (kernels_cluster.cu, fwd_sweep)
+    return (size_t)B * p.g.ns * (size_t)p.nt * p.g.level + (size_t)kClusterRowsMax * p.g.pitch;
 }
 
 int check_segment(const Plan &p, int segment)
@@ -533,7 +539,7 @@ int rdfwi_backward(rdfwi_plan plan, const float *v, int32_t B, const float *cot,
     ClusterConfig cc;
     const_cast<Plan &>(p).last_split = (!ckpt && w.split) ? (w.recompute ? 2 : 1) : 0;
     const_cast<Plan &>(p).last_u_chunk = w.u_chunk;
-    if (!ckpt && w.split && p.imaging != 1 && cluster_config(p, &cc, w.recompute ? std::min(w.u_chunk, B * g.ns) : B * g.ns, true)) {
+    if (!ckpt && w.resident && cluster_config(p, &cc, w.recompute ? std::min(w.u_chunk, B * g.ns) : B * g.ns, true)) {
         // resident imaging: ONE cluster-resident kernel per launch runs the adjoint field and forms the imaging sums in the
         // sweep (accumulators in tensor memory), reading the forward history once; no adjoint-field history, no imaging pass
         const int nshots = B * g.ns;

@@ -62,8 +62,8 @@ struct Plan {
     int cluster_size = 0;   // 0 = smallest cluster that fits
     int cluster_rows = 0;   // rows marched per thread of k_fwd_cluster: 0 = auto (13; 7 or 4 on wider clusters for few shots)
     int adj_mode = 0;         // 0 = auto (split: cluster u-field kernel + streaming imaging kernel), 1 = fused per-level adjoint (k_adj_step)
-    int imaging = 1;          // cluster engine: where the imaging sums are formed -- 1 = streaming kernel over two histories
-                              // (split adjoint), 2 = inside the adjoint sweep, accumulators in tensor memory; 0 = auto
+    int imaging = 0;          // cluster engine: where the imaging sums are formed -- 0 / 2 = inside the adjoint sweep, accumulators
+                              // in tensor memory (default), 1 = streaming kernel over two histories (the split adjoint)
     int perturb = 0;          // debug: seed of the schedule perturbation of k_fwd_cluster (0 = off), see rdfwi.h
     int img_prefetch = 0;     // imaging kernel: levels ahead pulled into L2 (0 = default 4)
     long long *trace_ptr = nullptr;  // debug: device buffer for per-warp timeline stamps of k_fwd_cluster

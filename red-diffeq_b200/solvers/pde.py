@@ -245,8 +245,8 @@ class FWIForward(nn.Module):
 
     def _choose_segment(self, plan, B, device):
         """History policy of one forward/backward pair: returns (segment, extras) and leaves the plan in that state.
-        Automatic mode walks the tiers until the buffers fit the free HBM: (1) every level + split adjoint (needs a
-        scratch history of the adjoint field); (2) no history at all: the backward pass recomputes the forward field
+        Automatic mode walks the tiers until the buffers fit the free HBM: (1) every level (the split adjoint, option
+        imaging = 1, also needs a scratch history of the adjoint field); (2) no history at all: the backward pass recomputes the forward field
         chunk by chunk on the cluster engine (segment = nt, one extra forward, two scratch histories of one or two waves
         of shots); (3) every level + fused per-level adjoint (no scratch); (4) history checkpointed in time on the
         per-level engine."""
@@ -275,8 +275,10 @@ class FWIForward(nn.Module):
             if clustered and "adj_mode" not in user:
                 # a record so long that the scratch history of the split adjoint holds less than a wave of shots leaves
                 # most SMs idle in every chunk: recomputing the forward field chunk by chunk is faster than that
+                # (only the split adjoint, option imaging = 1, has that scratch history: by default the imaging sums are
+                # formed inside the adjoint sweep and a full history that fits is always the fastest tier)
                 per_shot = 4.0 * plan.nt * plan.level_floats()
-                if int(40e9 // per_shot) < min(wave, B * plan.ns):
+                if user.get("imaging", 0) == 1 and int(40e9 // per_shot) < min(wave, B * plan.ns):
                     tiers = []
                 tiers.append((plan.nt, {}))
                 if "u_chunk_shots" not in user:

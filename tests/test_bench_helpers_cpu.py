@@ -17,6 +17,9 @@ def test_kernel_classes_from_ncu_names():
     assert c("void rdfwi::<unnamed>::k_fwd_cluster<13, 432, 1>(rdfwi::ClusterFwdArgs, rdfwi::Grid)") == "adjoint_field"
     assert c("void rdfwi::<unnamed>::k_fwd_cluster<(int)7, (int)0, (bool)1>(rdfwi::ClusterFwdArgs, rdfwi::Grid)") == "adjoint_field"
     assert c("void rdfwi::<unnamed>::k_fwd_cluster<13, 312, 0, 512>(rdfwi::ClusterFwdArgs, rdfwi::Grid)") == "forward"   # round-1 lists
+    assert c("void rdfwi::<unnamed>::k_fwd_cluster<13, 312, 2, 0>(rdfwi::ClusterFwdArgs, rdfwi::Grid)") == "adjoint_resident"
+    assert c("void rdfwi::<unnamed>::k_fwd_cluster<(int)7, (int)432, (int)2, (bool)0>(rdfwi::ClusterFwdArgs, rdfwi::Grid)") == "adjoint_resident"
+    assert c("void rdfwi::<unnamed>::k_fwd_cluster<(int)7, (int)432, (int)1, (bool)0>(rdfwi::ClusterFwdArgs, rdfwi::Grid)") == "adjoint_field"
     assert c("void rdfwi::<unnamed>::k_step_tile<4, 0>(rdfwi::StepArgs, rdfwi::Grid)") == "forward"
     assert c("void rdfwi::<unnamed>::k_step_tile<4, 1>(rdfwi::StepArgs, rdfwi::Grid)") == "adjoint_field"
     assert c("rdfwi::<unnamed>::k_imaging(const float *, ...)") == "imaging"
@@ -30,7 +33,7 @@ def test_committed_launch_lists_parse_and_hold_every_class():
     for workload, path in bench.TRAFFIC_PROFILES.items():
         assert os.path.exists(os.path.join(ROOT, path)), f"{path} (roofline.traffic of {workload}) is not committed"
         prof = bench.load_traffic_profile(path)
-        assert {"forward", "adjoint_field", "imaging"} <= set(prof), (workload, sorted(prof))
+        assert "forward" in prof and ("adjoint_resident" in prof or {"adjoint_field", "imaging"} <= set(prof)), (workload, sorted(prof))
         for cls, c in prof.items():
             assert c["bytes_per_launch"] > 1e6 and c["ncu_us_per_launch"] > 1.0, (workload, cls, c)
     r1 = bench.load_traffic_profile("profiles/launches_r1_v2_b64.csv")     # the round-1 list the judge recomputed from

@@ -61,7 +61,7 @@ def test_gradient_matches_reference(golden):
 @pytest.mark.parametrize("name", ["tiny_default", "tiny_custom", "tiny_half_receivers"])
 @pytest.mark.parametrize("rows", [1, 2, 4, 8])
 @pytest.mark.parametrize("chunk", [0, 1])
-@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "cluster-split", "cluster+per-level-fused"])
+@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "cluster-resident", "cluster-split", "cluster+per-level-fused"])
 def test_kernel_variants_agree_with_oracle(name, rows, chunk, engine, oracle):
     if not engine.startswith("per-level") and (rows != 1 or chunk != 0):
         pytest.skip("rows/chunk only affect the per-level engine")
@@ -72,6 +72,7 @@ def test_kernel_variants_agree_with_oracle(name, rows, chunk, engine, oracle):
     if engine == "per-level":
         op.set_option("u_chunk_shots", 3)                                 # several chunks even on the tiny cases
     if engine == "cluster-split":
+        op.set_option("imaging", 1)                                       # adjoint-field history + streaming imaging kernel
         op.set_option("u_chunk_shots", 2)                                 # several chunks even on the tiny cases
     op.set_option("rows_per_thread", rows)
     op.set_option("adj_rows_per_thread", 1 if rows in (1, 8) else 2)
@@ -108,15 +109,19 @@ def test_checkpointed_history_matches_full_history(name, segment):
 
 @pytest.mark.parametrize("name", ["tiny_default", "tiny_custom", "tiny_half_receivers", "openfwi"])
 @pytest.mark.parametrize("chunk", [0, 2])
-def test_recomputed_history_matches_full_history(name, chunk):
+@pytest.mark.parametrize("imaging", [0, 1])
+def test_recomputed_history_matches_full_history(name, chunk, imaging):
     """No history kept (segment = nt): the backward pass recomputes the forward field chunk by chunk on the cluster
-    engine and runs the split adjoint on it -- same kernels, same order => bit-identical to the full-history run."""
+    engine and runs the adjoint (resident imaging, or the split adjoint) on it -- same kernels, same order =>
+    bit-identical to the full-history run."""
     g = Golden(name)
     full = _op(g)
     full.set_option("engine", 2)
+    full.set_option("imaging", imaging)
     full.set_history_segment(0)
     rc = _op(g)
     rc.set_option("engine", 2)
+    rc.set_option("imaging", imaging)
     if chunk:
         rc.set_option("u_chunk_shots", chunk)
     rc.set_history_segment(g.ctx["nt"])
@@ -125,7 +130,7 @@ def test_recomputed_history_matches_full_history(name, chunk):
     s0, g0 = _run(full, g.v, cot)
     s1, g1 = _run(rc, g.v, cot)
     plan = rc._plan_for(g.v.shape[2], g.v.shape[3], torch.device("cuda:0"))
-    assert plan.get("adj_split") == 2 and plan.history_bytes(g.v.shape[0], g.ctx["nt"]) == 0
+    assert plan.get("adj_split") == (2 if imaging == 1 else 5) and plan.history_bytes(g.v.shape[0], g.ctx["nt"]) == 0
     assert np.array_equal(s0, s1)
     assert np.array_equal(g0, g1)
     assert rel_l2(g1, g.grad_f32) <= GRAD_TOL
@@ -174,7 +179,7 @@ def test_few_shots_pick_a_wide_cluster():
     assert np.array_equal(s16[3:4], s)
 
 
-@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "per-level-checkpointed", "cluster-split", "cluster+per-level-fused"])
+@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "per-level-checkpointed", "cluster-resident", "cluster-split", "cluster+per-level-fused"])
 def test_many_shots_per_model(engine, oracle):
     """More shots than any golden case (ns = 11: the per-level adjoint deals them over several grid.z slices, each with its
     own imaging plane; the cluster engines run more shots than fit one chunk)."""
@@ -188,6 +193,8 @@ def test_many_shots_per_model(engine, oracle):
     op = FWIForward(dict(ctx), "cuda:0", normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
     op.set_option("engine", 1 if engine.startswith("per-level") else 2)
     op.set_option("adj_mode", 1 if engine.endswith("fused") else 0)
+    if engine == "cluster-split":
+        op.set_option("imaging", 1)
     if engine in ("cluster-split", "per-level"):
         op.set_option("u_chunk_shots", 7)
     if engine == "per-level-checkpointed":
@@ -317,7 +324,7 @@ def test_errors():
 
 
 @pytest.mark.parametrize("nx,nbc", [(15, 9), (17, 9), (21, 10), (16, 8)])
-@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "cluster-split", "cluster+per-level-fused"])
+@pytest.mark.parametrize("engine", ["per-level", "per-level-fused", "cluster-resident", "cluster-split", "cluster+per-level-fused"])
 def test_odd_widths_against_oracle(nx, nbc, engine, oracle):
     """Padded widths with nxp % 4 in {1, 3, 0, ...}: the periodic image columns of the pitched layout (1..3 of them)
     must reproduce torch.roll's wrap-around bit for bit; no reference fixture has such a width, so the pinned oracle checks."""

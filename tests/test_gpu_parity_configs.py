@@ -34,9 +34,11 @@ def _phys(vn):
     return (vn + np.float32(1)) / np.float32(2) * np.float32(3000) + np.float32(1500)
 
 
-def test_overthrust_long_record_recompute_tier(oracle):
+@pytest.mark.parametrize("imaging", [0, 1])
+def test_overthrust_long_record_recompute_tier(oracle, imaging):
     """bench workload `overthrust_long` (BASELINE configs[3]: Overthrust grid = Marmousi grid, nt = 4000), one model, no
-    history kept: the backward pass recomputes the forward field chunk by chunk (adj_split == 2)."""
+    history kept: the backward pass recomputes the forward field chunk by chunk (adj_split == 5 with the imaging sums formed
+    in the adjoint sweep, 2 with the split adjoint)."""
     from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize
     from red_diffeq_b200.utils import synthetic
     ctx = _marmousi_ctx(nt=4000)
@@ -44,17 +46,20 @@ def test_overthrust_long_record_recompute_tier(oracle):
     sv = oracle.Survey(dict(ctx), 70, 190)
     cot = synthetic.cotangent((1, sv.ns, sv.nt_out, sv.nrec), seed=42)
     op = FWIForward(dict(ctx), "cuda:0", normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    op.set_option("imaging", imaging)
     op.set_history_segment(4000)
     seis, grad = _run(op, vn, cot)
     plan = op._plan_for(70, 190, torch.device("cuda:0"))
-    assert plan.get("adj_split") == 2 and plan.history_bytes(1, 4000) == 0
+    assert plan.get("adj_split") == (2 if imaging == 1 else 5) and plan.history_bytes(1, 4000) == 0
     seis_o, grad_o = oracle.gradient(sv, _phys(vn), cot)
     assert np.array_equal(seis, seis_o)
     assert rel_l2(grad, grad_o * 1500.0) <= GRAD_TOL
-    # the automatic policy on the bench's batch of 8 picks the same tier (8 x 5 x 2.1 GB of history per 1000 levels x 4)
+    # the automatic policy on the bench's batch of 8: the split adjoint would hold less than a wave of shots in its scratch
+    # history and recomputes instead; with the imaging sums formed in the sweep the 85 GB history is kept
     auto = FWIForward(dict(ctx), "cuda:0", normalize=True, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
+    auto.set_option("imaging", imaging)
     seg, _ = auto._choose_segment(auto._plan_for(70, 190, torch.device("cuda:0")), 8, torch.device("cuda:0"))
-    assert seg in (0, 4000)
+    assert seg == (4000 if imaging == 1 else 0)
     op.release_memory()
 
 

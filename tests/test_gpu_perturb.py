@@ -9,7 +9,8 @@ to ~4 us, a whole level's duration, on a quarter of the (warp, level, site) trip
 point of a level: the halo waits, the sweep with its early halo pushes, the late pushes, the bulk-copy hand-over and the
 sampling / cotangent warp.  Every seed gives a different schedule; a missing ordering shows up as a changed bit.
 
-Each configuration (cluster size x rows per thread, forward and adjoint-field mode) is run unperturbed once and then
+Each configuration (cluster size x rows per thread; forward mode, adjoint mode with the imaging sums formed in the sweep --
+accumulators in tensor memory, forward rows staged by cp.async -- and the split adjoint's adjoint-field mode) is run unperturbed once and then
 under several seeds: seismograms and gradients must be bit-identical every time.
 """
 import numpy as np
@@ -21,12 +22,13 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-def _op(g, rows, csize):
+def _op(g, rows, csize, imaging=0):
     from red_diffeq_b200 import FWIForward, s_normalize_none, v_denormalize
     op = FWIForward(g.fresh_ctx(), "cuda:0", sample_temporal=g.sample_temporal, sample_spatial=g.sample_spatial,
                     normalize=g.normalize, v_denorm_func=v_denormalize, s_norm_func=s_normalize_none)
     op.set_option("engine", 2)
     op.set_option("cluster_rows", rows)
+    op.set_option("imaging", imaging)   # 0: imaging sums formed in the adjoint sweep (tensor memory), 1: split adjoint
     if csize:
         op.set_option("cluster_size", csize)
     return op
@@ -39,19 +41,20 @@ def _run(op, v_np, cot_np):
     return seis.detach().cpu().numpy(), v.grad.cpu().numpy()
 
 
-CASES = [  # fixture, rows per thread, cluster size (0 = smallest that fits), seeds
-    ("tiny_default", 13, 0, 20), ("tiny_default", 4, 3, 20), ("tiny_default", 7, 2, 20), ("tiny_default", 4, 5, 20),
-    ("tiny_custom", 7, 2, 20), ("tiny_custom", 13, 4, 20), ("tiny_half_receivers", 4, 5, 20), ("tiny_half_receivers", 7, 3, 20),
-    ("tiny_half_receivers", 13, 2, 20),
-    ("openfwi", 13, 0, 6), ("openfwi", 7, 0, 6), ("openfwi", 4, 0, 6), ("openfwi", 13, 6, 4),
-    ("marmousi", 13, 0, 6), ("marmousi", 7, 0, 6), ("marmousi", 13, 8, 4),
+CASES = [  # fixture, rows per thread, cluster size (0 = smallest that fits), seeds, imaging option
+    ("tiny_default", 13, 0, 20, 0), ("tiny_default", 4, 3, 20, 0), ("tiny_default", 7, 2, 20, 0), ("tiny_default", 4, 5, 20, 0),
+    ("tiny_custom", 7, 2, 20, 0), ("tiny_custom", 13, 4, 20, 0), ("tiny_half_receivers", 4, 5, 20, 0), ("tiny_half_receivers", 7, 3, 20, 0),
+    ("tiny_half_receivers", 13, 2, 20, 0),
+    ("openfwi", 13, 0, 6, 0), ("openfwi", 7, 0, 6, 0), ("openfwi", 4, 0, 6, 0), ("openfwi", 13, 6, 4, 0),
+    ("marmousi", 13, 0, 6, 0), ("marmousi", 7, 0, 6, 0), ("marmousi", 13, 8, 4, 0),
+    ("tiny_default", 13, 0, 10, 1), ("tiny_custom", 7, 2, 10, 1), ("openfwi", 13, 0, 4, 1), ("marmousi", 7, 0, 4, 1),
 ]
 
 
-@pytest.mark.parametrize("name,rows,csize,seeds", CASES)
-def test_perturbed_schedules_are_bit_identical(name, rows, csize, seeds):
+@pytest.mark.parametrize("name,rows,csize,seeds,imaging", CASES)
+def test_perturbed_schedules_are_bit_identical(name, rows, csize, seeds, imaging):
     g = Golden(name)
-    op = _op(g, rows, csize)
+    op = _op(g, rows, csize, imaging)
     ns, nrec = len(op.ctx["sx"]), len(op.ctx["gx"])
     cot = g.cotangent((g.v.shape[0], ns, -(-g.ctx["nt"] // g.sample_temporal), nrec))
     s0, g0 = _run(op, g.v, cot)

@@ -48,7 +48,7 @@ def main():
     ok = True
     for name in [c for c in args.cases.split(",") if c]:
         g = Golden(name)
-        base = make_op(g, engine=2, imaging=1)
+        base = make_op(g, engine=2, imaging=1, cluster_rows=13 if os.environ.get("RDFWI_LIB") else 0)
         shape = (g.v.shape[0], len(base.ctx["sx"]), -(-g.ctx["nt"] // g.sample_temporal), len(base.ctx["gx"]))
         cot = g.cotangent(shape)
         s1, g1 = run(base, g.v, cot)

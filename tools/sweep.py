@@ -73,10 +73,10 @@ def run_case(n, ns, B, nt, peak, dev, rank, world):
     seg = plan.get("history_segment")
     clustered = plan.get("cluster_size_used") and OPTS.get("engine") != 1
     sp = plan.get("adj_split")
-    eng_f = "cluster C=%d R=%d" % (plan.get("cluster_size_last"), plan.get("cluster_rows_last")) if clustered and (not seg or sp == 2) else "per-level"
-    eng_a = {1: "cluster split", 2: "cluster split, forward recomputed", 3: "per-level split (chunks of %d shots)" % plan.get("u_chunk_used")}.get(sp) or "per-level fused"
+    eng_f = "cluster C=%d R=%d" % (plan.get("cluster_size_last"), plan.get("cluster_rows_last")) if clustered and (not seg or sp in (2, 5)) else "per-level"
+    eng_a = {1: "cluster split", 2: "cluster split, forward recomputed", 4: "cluster resident (TMEM imaging)", 5: "cluster resident, forward recomputed", 3: "per-level split (chunks of %d shots)" % plan.get("u_chunk_used")}.get(sp) or "per-level fused"
     op.release_memory()
-    hist = "none (recomputed)" if sp == 2 else ("checkpoint K=%d" % seg if seg else "full")
+    hist = "none (recomputed)" if sp in (2, 5) else ("checkpoint K=%d" % seg if seg else "full")
     return dict(n=n, ns=ns, B=B, nt=nt, forward_ms=f_ms, adjoint_ms=a_ms, pairs_per_s=rate, frac=rate * 28 / (world * peak * 1e9),
                 engine_fwd=eng_f, engine_adj=eng_a, history=hist, gpus=world, shots_per_rank=ns_local)
 
