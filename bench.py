@@ -62,10 +62,10 @@ WORKLOADS = {
 # --clock-control none --csv ... python bench.py --only-headline --workload W`), committed under profiles/: the source of
 # `roofline.traffic` (DRAM bytes of ONE launch of a kernel class).  Not measured in the bench run itself -- the key says so.
 TRAFFIC_PROFILES = {
-    "openfwi_b64": "profiles/launches_r2_openfwi_b64.csv",
-    "marmousi_b1": "profiles/launches_r2_marmousi_b1.csv",
-    "marmousi_sharded": "profiles/launches_r2_marmousi_sharded.csv",
-    "overthrust_long": "profiles/launches_r2_overthrust_long.csv",
+    "openfwi_b64": "profiles/launches_r2b_openfwi_b64.csv",
+    "marmousi_b1": "profiles/launches_r2b_marmousi_b1.csv",
+    "marmousi_sharded": "profiles/launches_r2b_marmousi_sharded.csv",
+    "overthrust_long": "profiles/launches_r2b_overthrust_long.csv",
 }
 
 

@@ -187,6 +187,8 @@ struct ImgThread {
     const float *pg;  // global: this thread's float4 of its first marching row of the forward level paired with this sweep
     uint32_t tm;      // TMEM address of the thread's columns: Ga [0, 4R), Gk [4R, 8R), alpha of the last ATM rows [8R, ..)
     float *ring;      // the thread's first 16-byte slot in shared memory (the second one is `threads` slots further)
+    bool first, next; // first level of a shot (its first two rows are not in flight yet) / a further level follows
+    size_t level;     // floats per level of the history
 };
 
 // ---- mbarrier + bulk load (global -> shared), used to stream the forward history into the adjoint

@@ -50,10 +50,13 @@ namespace {
 // slots in shared memory and fills them with cp.async two rows ahead: asynchronous, no registers, no scheduler to argue
 // with; the slab of the level three sweeps ahead is pulled into L2 by one bulk prefetch per level.
 #ifndef RDFWI_IMG_PF
-#define RDFWI_IMG_PF 3
+#define RDFWI_IMG_PF 1
 #endif
 constexpr int kImgPrefetchLevels = RDFWI_IMG_PF;
-template <int RMAX, int PITCH, int DIR, bool EXACT, bool IMG, int ATM>
+// CTM (forward mode): the two time-invariant coefficient rows of a cell -- alpha and t1 = (2 - 5 alpha) - kappa, both
+// rounded exactly as the reference rounds them -- live in tensor memory (104 columns per thread) instead of 52 registers
+// for alpha plus four instructions per cell pair and level recomputing t1.
+template <int RMAX, int PITCH, int DIR, bool EXACT, bool IMG, int ATM, bool CTM>
 __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cur, const int prv, const int kap_off,
                                           const int pitch_rt, const int l0, const SweepThread &th,
                                           const float4 (&al)[RMAX], const float (&kapx)[4], const HaloPush &hp,
@@ -71,10 +74,13 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
     const int nvalid = th.lb - th.la;
     // forward-history rows of the thread, two in flight (rows the thread does not own re-read its first row: in bounds)
     const uint32_t ring0 = IMG ? smem_u32(im.ring) : 0, ring1 = ring0 + kClusterThreads * 16;
-    if (IMG) {  // rows the thread does not own are fetched all the same (immediate offsets: no address arithmetic per row);
-                // they lie inside the history or the kClusterRowsMax rows of padding behind it, their sums are never written out
-        cp_async16_commit(ring0, im.pg);
+    if (IMG && im.first) {
+        // rows the thread does not own are fetched all the same (immediate offsets: no address arithmetic per row); they lie
+        // inside the history or the kClusterRowsMax rows of padding behind it, their sums are never written out.
+        // (Only the first level of a shot starts its copies here: every other level's first two rows were requested by
+        // the sweep before it, as soon as their slots were free -- see the end of the row loop.)
         cp_async16_commit(ring1, im.pg + P);
+        cp_async16_commit(ring0, im.pg);
     }
 
     float4 w0 = ld4(cb - 2 * P), w1 = ld4(cb - P), w2 = ld4(cb), w3 = ld4(cb + P);
@@ -87,10 +93,18 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             tm_ld4(im.tm + 4 * RMAX + 4 * r, gk);
             if (r >= RMAX - ATM) tm_ld4(im.tm + 8 * RMAX + 4 * (r - (RMAX - ATM)), alt);
             const uint32_t slot = (r & 1) ? ring1 : ring0;
-            if (r + 1 < RMAX) cp_async_wait<1>();  // this row's copy has landed (the next row's may be in flight)
-            else cp_async_wait<0>();
+            // this row's copy has landed (the next one's may be in flight).  Commit order with 13 rows: ... row 11, row 12,
+            // then the next level's row 1 (its slot is free after row 11) and row 0 (after row 12) -- hence row 0 waits for all.
+            // (The last row of a shot's last level has nothing committed behind it either.)
+            if (r == 0 || (r == RMAX - 1 && !im.next)) cp_async_wait<0>();
+            else cp_async_wait<1>();
             pv = lds4_volatile(slot);
             if (r + 2 < RMAX) cp_async16_commit(slot, im.pg + (r + 2) * P);
+            else if (im.next) cp_async16_commit(slot, im.pg - im.level + (r & 1) * P);  // forward level t-1: the row of this slot's parity
+        }
+        if (CTM) {
+            tm_ld4(im.tm + 4 * r, ga);              // alpha row
+            tm_ld4(im.tm + 4 * RMAX + 4 * r, gk);   // t1 row
         }
         const float4 w4 = ld4(cb + (r + 2) * P);
         const float4 old = ld4(pb + r * P);
@@ -119,7 +133,9 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             if (r >= RMAX - ATM) tm_wait_ld(ga, gk, alt);
             else tm_wait_ld(ga, gk);
         }
-        const float4 alr = (IMG && r >= RMAX - ATM) ? make_float4(alt[0], alt[1], alt[2], alt[3]) : al[r];
+        if (CTM) tm_wait_ld(ga, gk);
+        const float4 alr = CTM ? make_float4(ga[0], ga[1], ga[2], ga[3])
+                               : ((IMG && r >= RMAX - ATM) ? make_float4(alt[0], alt[1], alt[2], alt[3]) : al[r]);
         // Two cells per instruction for the twelve additions of a cell (FADD2, IEEE round-to-nearest per lane, same
         // association as the reference); the six multiplications stay scalar so that ptxas cannot contract them
         // into FFMA2 (it does contract packed products, even with .rn) -- seismograms stay bit-identical.
@@ -143,7 +159,8 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             if (EXACT) {  // forward wavefield: one rounding per reference op, products never packed (see above)
                 const float2 lap = f2add(make_float2(__fmul_rn(c2, s1.x), __fmul_rn(c2, s1.y)),
                                          make_float2(__fmul_rn(c3, s2.x), __fmul_rn(c3, s2.y)));
-                const float2 t1 = f2sub(f2add(make_float2(2.0f, 2.0f), make_float2(__fmul_rn(-5.0f, alp.x), __fmul_rn(-5.0f, alp.y))), kp);
+                const float2 t1 = CTM ? make_float2(gk[j], gk[j + 1])
+                                      : f2sub(f2add(make_float2(2.0f, 2.0f), make_float2(__fmul_rn(-5.0f, alp.x), __fmul_rn(-5.0f, alp.y))), kp);
                 const float2 t2 = f2sub(make_float2(1.0f, 1.0f), kp);
                 const float2 a1 = make_float2(__fmul_rn(t1.x, e[j + 2]), __fmul_rn(t1.y, e[j + 3]));
                 const float2 a2 = make_float2(__fmul_rn(t2.x, oldp.x), __fmul_rn(t2.y, oldp.y));
@@ -218,6 +235,11 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     constexpr int NT = kClusterThreads;
     constexpr bool ADJ = MODE >= 1, IMG = MODE == 2;
     // alpha rows kept in tensor memory beside the 8 accumulator columns per row (128 columns per thread)
+#ifdef RDFWI_NO_FWD_TMEM
+    constexpr bool CTM = false;
+#else
+    constexpr bool CTM = MODE == 0;   // forward mode: alpha and t1 rows in tensor memory (see fwd_sweep)
+#endif
     constexpr int ATM = !IMG ? 0 : ((128 - 8 * RMAX) / 4 < RMAX ? (128 - 8 * RMAX) / 4 : RMAX);
     static_assert(!IMG || 8 * RMAX + 4 * ATM <= 128, "tensor-memory columns per thread");
     extern __shared__ __align__(128) float smem[];
@@ -317,15 +339,17 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
         for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
     }
     uint32_t tm = 0;
-    if (IMG) {
+    if (IMG || CTM) {
         if (tid < 32) tm_alloc_all(&s_tmem);
         tm_fence_before_sync();
         __syncthreads();
         tm_fence_after_sync();
         tm = s_tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * 128);
+        if (IMG) {
 #pragma unroll
-        for (int c = 0; c < 8 * RMAX; c += 4) tm_st4(tm + c, 0.f, 0.f, 0.f, 0.f);
-        tm_wait_st();
+            for (int c = 0; c < 8 * RMAX; c += 4) tm_st4(tm + c, 0.f, 0.f, 0.f, 0.f);
+            tm_wait_st();
+        }
     }
     for (int i = tid; i <= g.nxp; i += NT) s_rec_ptr[i] = a.rec_ptr[i];
     for (int i = tid; i < g.nrec; i += NT) s_rec_idx[i] = a.rec_idx[i];
@@ -349,10 +373,11 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
         for (int r = 0; r < RMAX; ++r) {
             const int lrow = rev ? l0 - r : l0 + r;
             const float4 av = (lrow >= th.la && lrow < th.lb) ? ld4(a.alpha + (size_t)b * g.level + (size_t)(r0 + lrow) * pitch + th.x) : zero4;
-            if (r < RMAX - ATM) al[r] = av;
+            if (CTM) tm_st4(tm + 4 * r, av.x, av.y, av.z, av.w);
+            else if (r < RMAX - ATM) al[r] = av;
             else tm_st4(tm + 8 * RMAX + 4 * (r - (RMAX - ATM)), av.x, av.y, av.z, av.w);
         }
-        if (IMG && ATM > 0) tm_wait_st();
+        if ((IMG && ATM > 0) || CTM) tm_wait_st();
         float kapx[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -421,6 +446,26 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                 l2_prefetch_bulk(ph_shot + (size_t)(a.nt - 1 - d) * g.level + (size_t)r0 * pitch, (uint32_t)(nrows * pitch * sizeof(float)));
         __syncthreads();
         cluster_sync_all();  // shot boundary: every CTA has finished the previous shot and cleared its buffers
+        if (CTM && warp_active) {
+            // t1 = (2 + (-5 alpha)) - kappa per cell, one rounding per reference operation (solvers/pde.py:69), kappa selected
+            // as in the sweep; the sponge row table was written before the barrier above
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                float av[4];
+                tm_ld4(tm + 4 * r, av);
+                const float kapz = smem[kap_off + (rev ? l0 - r : l0 + r)];
+                float dummy[4] = {0.f, 0.f, 0.f, 0.f};
+                tm_wait_ld(av, dummy);
+                float t1[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float kp = __fmaf_rn(th.mz[j], kapz, kapx[j]);
+                    t1[j] = __fsub_rn(__fadd_rn(2.0f, __fmul_rn(-5.0f, av[j])), kp);
+                }
+                tm_st4(tm + 4 * RMAX + 4 * r, t1[0], t1[1], t1[2], t1[3]);
+            }
+            tm_wait_st();
+        }
 
         // one time level: p_{t-1} in buffer `cur`, p_{t-2} in `prv`, p_t overwrites p_{t-2}
         // optional per-warp timeline (debug option "trace_ptr"): clock64 stamps of levels 100..103 of cluster 0's first shot
@@ -467,8 +512,11 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
                 im.pg = IMG ? ph_shot + (size_t)trev * g.level + (size_t)(r0 + l0) * pitch + th.x : nullptr;
                 im.tm = tm;
                 im.ring = s_ring + tid * 4;
-                if (rev) fwd_sweep<RMAX, PITCH, -1, !ADJ, IMG, ATM>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends, im);
-                else fwd_sweep<RMAX, PITCH, 1, !ADJ, IMG, ATM>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends, im);
+                im.first = t == 0;
+                im.next = trev > 0;
+                im.level = (size_t)g.level;
+                if (rev) fwd_sweep<RMAX, PITCH, -1, !ADJ, IMG, ATM, CTM>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends, im);
+                else fwd_sweep<RMAX, PITCH, 1, !ADJ, IMG, ATM, CTM>(smem, cur, prv, kap_off, pitch, l0, th, al, kapx, hp, push_bar, hp.early && sends, im);
                 stamp(t, 2);
                 jitter<PERT>(a.perturb, 2, (unsigned)t);
                 if (ADJ) {
@@ -571,7 +619,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     }
     if (tid == 0) bulk_wait_all();
     cluster_sync_all();  // no CTA exits while a neighbour may still address its shared memory
-    if (IMG && tid < 32) tm_free_all(s_tmem);
+    if ((IMG || CTM) && tid < 32) tm_free_all(s_tmem);
 }
 
 }  // namespace
@@ -722,8 +770,8 @@ static cudaError_t dispatch_fwd_cluster(const Plan &p, const ClusterConfig &cc, 
         case kClusterRowsMax: return dispatch_fwd_cluster_r<kClusterRowsMax>(p, cc, a, st, wave_only);
 #ifndef RDFWI_DEV_FAST
         case 7: return dispatch_fwd_cluster_r<7>(p, cc, a, st, wave_only);
-        case 4: return dispatch_fwd_cluster_r<4>(p, cc, a, st, wave_only);
 #endif
+        case 4: return dispatch_fwd_cluster_r<4>(p, cc, a, st, wave_only);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -92,6 +92,7 @@ def main():
                 torch.cuda.synchronize()
                 t1 = time.perf_counter()
             grad = v.grad.clone()
+            print(f"   seismogram bit checksum {int(seis.view(torch.int32).to(torch.int64).sum().item())}  gradient sum {float(grad.double().sum()):.9e}")
             print(f"B={B} imaging={mode} {extra}: backward {1e3 * (t1 - t0):.2f} ms  adj_split={pget(op, 'adj_split')}  C={pget(op, 'cluster_size_last')} R={pget(op, 'cluster_rows_last')}"
                   f"  kernel us/launch: " + ", ".join(f"{k} {pget(op, 'us_' + k) / max(1, pget(op, 'n_' + k)):.0f}" for k in ("forward", "adjoint_field", "imaging", "adjoint_resident")))
             if gref is None:
