@@ -53,6 +53,8 @@ namespace {
 #define RDFWI_IMG_PF 1
 #endif
 constexpr int kImgPrefetchLevels = RDFWI_IMG_PF;
+// 16-byte shared-memory slots per thread staging the forward rows of the resident imaging (see fwd_sweep)
+__host__ __device__ constexpr int img_ring_slots(const int rows) { return rows <= 7 ? rows : 2; }
 // CTM (forward mode): the two time-invariant coefficient rows of a cell -- alpha and t1 = (2 - 5 alpha) - kappa, both
 // rounded exactly as the reference rounds them -- live in tensor memory (104 columns per thread) instead of 52 registers
 // for alpha plus four instructions per cell pair and level recomputing t1.
@@ -72,15 +74,23 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
     const float *kz = smem + kap_off + l0;
     const float *push_dst = smem + prv + hp.dst + th.x;
     const int nvalid = th.lb - th.la;
-    // forward-history rows of the thread, two in flight (rows the thread does not own re-read its first row: in bounds)
+    // Forward-history rows of the thread.  Wide clusters with few rows per thread (launches of few shots) have room for one
+    // slot per row: every row of level t-1 is requested while level t is swept, a whole level ahead (a 4-row sweep is shorter
+    // than two L2 round trips).  The throughput configuration (13 rows, shared memory full) has two slots, two rows ahead.
+    constexpr int RING = img_ring_slots(RMAX);
     const uint32_t ring0 = IMG ? smem_u32(im.ring) : 0, ring1 = ring0 + kClusterThreads * 16;
     if (IMG && im.first) {
         // rows the thread does not own are fetched all the same (immediate offsets: no address arithmetic per row); they lie
         // inside the history or the kClusterRowsMax rows of padding behind it, their sums are never written out.
-        // (Only the first level of a shot starts its copies here: every other level's first two rows were requested by
-        // the sweep before it, as soon as their slots were free -- see the end of the row loop.)
-        cp_async16_commit(ring1, im.pg + P);
-        cp_async16_commit(ring0, im.pg);
+        // (Only the first level of a shot starts its copies here: every other level's first rows were requested by the
+        // sweep before it, as soon as their slots were free -- see the row loop.)
+        if (RING == 2) {
+            cp_async16_commit(ring1, im.pg + P);
+            cp_async16_commit(ring0, im.pg);
+        } else {
+#pragma unroll
+            for (int q = 0; q < RMAX; ++q) cp_async16_commit(ring0 + q * (kClusterThreads * 16), im.pg + q * P);
+        }
     }
 
     float4 w0 = ld4(cb - 2 * P), w1 = ld4(cb - P), w2 = ld4(cb), w3 = ld4(cb + P);
@@ -92,15 +102,22 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             tm_ld4(im.tm + 4 * r, ga);
             tm_ld4(im.tm + 4 * RMAX + 4 * r, gk);
             if (r >= RMAX - ATM) tm_ld4(im.tm + 8 * RMAX + 4 * (r - (RMAX - ATM)), alt);
-            const uint32_t slot = (r & 1) ? ring1 : ring0;
-            // this row's copy has landed (the next one's may be in flight).  Commit order with 13 rows: ... row 11, row 12,
-            // then the next level's row 1 (its slot is free after row 11) and row 0 (after row 12) -- hence row 0 waits for all.
-            // (The last row of a shot's last level has nothing committed behind it either.)
-            if (r == 0 || (r == RMAX - 1 && !im.next)) cp_async_wait<0>();
-            else cp_async_wait<1>();
-            pv = lds4_volatile(slot);
-            if (r + 2 < RMAX) cp_async16_commit(slot, im.pg + (r + 2) * P);
-            else if (im.next) cp_async16_commit(slot, im.pg - im.level + (r & 1) * P);  // forward level t-1: the row of this slot's parity
+            if (RING == 2) {
+                const uint32_t slot = (r & 1) ? ring1 : ring0;
+                // this row's copy has landed (the next one's may be in flight).  Commit order with 13 rows: ... row 11, row 12,
+                // then the next level's row 1 (its slot is free after row 11) and row 0 (after row 12) -- hence row 0 waits for
+                // all.  (The last row of a shot's last level has nothing committed behind it either.)
+                if (r == 0 || (r == RMAX - 1 && !im.next)) cp_async_wait<0>();
+                else cp_async_wait<1>();
+                pv = lds4_volatile(slot);
+                if (r + 2 < RMAX) cp_async16_commit(slot, im.pg + (r + 2) * P);
+                else if (im.next) cp_async16_commit(slot, im.pg - im.level + (r & 1) * P);  // forward level t-1: the row of this slot's parity
+            } else {
+                const uint32_t slot = ring0 + r * (kClusterThreads * 16);
+                if (r == 0) cp_async_wait<0>();  // all rows of this level were requested during the previous sweep
+                pv = lds4_volatile(slot);
+                if (im.next) cp_async16_commit(slot, im.pg - im.level + r * P);
+            }
         }
         if (CTM) {
             tm_ld4(im.tm + 4 * r, ga);              // alpha row
@@ -247,12 +264,18 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
 
     const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
     const int cid = blockIdx.x / C, ncl = gridDim.x / C;
+    // rows of the grid dealt over the CTAs of the cluster: nzp / C each, the remainder one row each to the first CTAs -- or
+    // to the last ones (a.rows_flip, chosen by cluster_rows_flip()) when that keeps the source / receiver row two rows away
+    // from every slab edge: a CTA whose patched row is an edge row cannot push its halo rows from inside the sweep, and
+    // when a launch has few shots its neighbours (and theirs ...) spend a third of every level waiting for them
     const int base = g.nzp / C, rem = g.nzp % C;
-    const int nrows = base + (rank < rem ? 1 : 0);
-    const int r0 = rank * base + (rank < rem ? rank : rem);
+    const int first_long = a.rows_flip ? C - rem : 0;  // CTAs first_long .. first_long + rem - 1 have base + 1 rows
+    auto rows_of = [&](const int k) { return base + ((k >= first_long && k < first_long + rem) ? 1 : 0); };
+    const int nrows = rows_of(rank);
+    const int r0 = rank * base + (rank <= first_long ? 0 : (rank - first_long < rem ? rank - first_long : rem));
     const int up = rank == 0 ? C - 1 : rank - 1;
     const int dn = rank == C - 1 ? 0 : rank + 1;
-    const int nrows_up = base + (up < rem ? 1 : 0);
+    const int nrows_up = rows_of(up);
 
     const int pitch = PITCH > 0 ? PITCH : g.pitch;
     const int slab = (a.slabrows + 4) * pitch;  // floats per buffer: 2 halo rows, slab rows, 2 halo rows
@@ -265,11 +288,12 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     float *s_ginj = s_prow + 2 * pitch;                   // [pitch] sum_t p_t[rec] g_t per column (MODE 2)
     int *s_rec_ptr = reinterpret_cast<int *>(s_ginj + pitch);
     int *s_rec_idx = s_rec_ptr + g.nxp + 1;
-    float *s_cot = reinterpret_cast<float *>(s_rec_idx + g.nrec);  // [2][nxp] per-column cotangent sums (adjoint mode)
+    int *s_rec_col = s_rec_idx + g.nrec;  // padded column of every receiver (the survey's igx)
+    float *s_cot = reinterpret_cast<float *>(s_rec_col + g.nrec);  // [2][nxp] per-column cotangent sums (adjoint mode)
     float *s_raw = s_cot + 2 * g.nxp;  // [2][nrec] cotangent rows as they sit in HBM, landed by cp.async (adjoint mode)
     float *s_wav = s_raw + 2 * g.nrec;
-    const bool wav_in_smem = a.wav_smem != 0;  // (never in MODE 2: the ring takes the room)
-    float *s_ring = smem + (((int)(s_wav - smem) + 3) & ~3);  // MODE 2: [2][threads] 16-byte slots, see fwd_sweep
+    const bool wav_in_smem = a.wav_smem != 0;
+    float *s_ring = smem + (((int)(s_wav - smem) + (wav_in_smem ? a.nt : 0) + 3) & ~3);  // MODE 2: [slots][threads] 16 bytes, see fwd_sweep
     const bool st1 = a.st == 1;  // every level is sampled (all configs of the reference): no integer division on the level's critical path
 
     const int tid = threadIdx.x, lane_id = tid & 31;
@@ -352,7 +376,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
         }
     }
     for (int i = tid; i <= g.nxp; i += NT) s_rec_ptr[i] = a.rec_ptr[i];
-    for (int i = tid; i < g.nrec; i += NT) s_rec_idx[i] = a.rec_idx[i];
+    for (int i = tid; i < g.nrec; i += NT) { s_rec_idx[i] = a.rec_idx[i]; s_rec_col[i] = a.rec_col[i]; }
+    if (ADJ)
+        for (int i = tid; i < 2 * g.nxp; i += NT) s_cot[i] = 0.0f;  // (receiver-major path: columns without a receiver stay 0)
+    const bool rec_simple = a.rec_simple != 0;  // at most one receiver per column (every configuration of the reference)
     if (wav_in_smem)
         for (int i = tid; i < a.nt; i += NT) s_wav[i] = a.wavelet[i];
     __syncthreads();
@@ -426,6 +453,19 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
             if (tr < 0 || (!st1 && tr % a.st != 0)) return;
             const float *raw = s_raw + buf * g.nrec;
             float *dst = s_cot + buf * g.nxp;
+            if (rec_simple) {
+                // receiver-major: independent iterations, three per lane for 70 receivers -- the column-major loop below is ten
+                // dependent shared-memory round trips per lane, 4 500 cycles per level on a warp that every level's barrier
+                // waits for: longer than a whole 4-row sweep when the launch has few shots (tools/trace_levels.py, round 2)
+#pragma unroll 2
+                for (int r = lane_id; r < g.nrec; r += 32) {
+                    const int xx = s_rec_col[r];
+                    const float c = raw[r];
+                    dst[xx] = c;
+                    if (IMG) s_ginj[xx] += c * s_prow[buf * pitch + xx];
+                }
+                return;
+            }
 #pragma unroll 4
             for (int xx = lane_id; xx < g.nxp; xx += 32) {
                 float acc = 0.0f;
@@ -567,8 +607,13 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
             if (!ADJ && a.seis != nullptr && tid >= NT - 32 && (st1 || t % a.st == 0) && g.igz >= r0 && g.igz < r0 + nrows) {
                 float *seis_t = a.seis + ((size_t)gshot * g.nt_out + (st1 ? t : t / a.st)) * g.nrec;
                 const float *row = smem + prv + (2 + g.igz - r0) * pitch;
-                for (int xx = lane_id; xx < g.nxp; xx += 32)
-                    for (int k = s_rec_ptr[xx]; k < s_rec_ptr[xx + 1]; ++k) seis_t[s_rec_idx[k]] = row[xx];
+                if (rec_simple) {
+#pragma unroll 2
+                    for (int r = lane_id; r < g.nrec; r += 32) seis_t[r] = row[s_rec_col[r]];  // coalesced
+                } else {
+                    for (int xx = lane_id; xx < g.nxp; xx += 32)
+                        for (int k = s_rec_ptr[xx]; k < s_rec_ptr[xx + 1]; ++k) seis_t[s_rec_idx[k]] = row[xx];
+                }
             }
             if (a.hist != nullptr && tid == 0)
                 bulk_store(a.hist + (size_t)shot * hist_shot + (size_t)t * g.level + (size_t)r0 * pitch,
@@ -644,11 +689,11 @@ static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, 
         const int ngroups = (maxrows + R - 1) / R;  // each thread marches R rows
         if (ngroups > groups_max) continue;
         const int slabrows = ngroups * R;  // >= maxrows: rows past the slab are computed but never stored
-        size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + 3 * g.pitch + g.nxp + 1 + g.nrec + 2 * g.nxp + 2 * g.nrec) * sizeof(float);
-        if (img) smem += 2 * kClusterThreads * 16 + 16;  // resident imaging: two 16-byte slots per thread for the forward rows
+        size_t smem = ((size_t)2 * (slabrows + 4) * g.pitch + slabrows + 16 + 3 * g.pitch + g.nxp + 1 + 2 * g.nrec + 2 * g.nxp + 2 * g.nrec) * sizeof(float);
+        if (img) smem += (size_t)img_ring_slots(R) * kClusterThreads * 16 + 16;  // resident imaging: slots staging the forward rows
         if (smem > (size_t)max_smem) continue;
         const size_t room = (size_t)max_smem;
-        cfg->wav_smem = !img && smem + (size_t)p.nt * sizeof(float) <= room;
+        cfg->wav_smem = smem + (size_t)p.nt * sizeof(float) <= room;
         if (cfg->wav_smem) smem += (size_t)p.nt * sizeof(float);
         cfg->img = img;
         cfg->nthreads = nthreads;
@@ -776,9 +821,31 @@ static cudaError_t dispatch_fwd_cluster(const Plan &p, const ClusterConfig &cc, 
     }
 }
 
+// Which CTAs of a C-CTA cluster take the nzp % C extra rows (0: the first ones, 1: the last ones): the choice that keeps the
+// source row and the receiver row at least two rows inside a slab, if there is one (see k_fwd_cluster).
+static int cluster_rows_flip(const Grid &g, const int C)
+{
+    const int base = g.nzp / C, rem = g.nzp % C;
+    auto on_edge = [&](const int flip, const int row) {
+        const int first_long = flip ? C - rem : 0;
+        for (int k = 0, r0 = 0; k < C; ++k) {
+            const int n = base + ((k >= first_long && k < first_long + rem) ? 1 : 0);
+            if (row >= r0 && row < r0 + n) return row - r0 < 2 || row - r0 >= n - 2;
+            r0 += n;
+        }
+        return false;
+    };
+    if (rem == 0) return 0;
+    const bool bad0 = on_edge(0, g.isz) || on_edge(0, g.igz), bad1 = on_edge(1, g.isz) || on_edge(1, g.igz);
+    return (bad0 && !bad1) ? 1 : 0;
+}
+
 cudaError_t launch_fwd_cluster(const Plan &p, const ClusterConfig &cc, ClusterFwdArgs a, cudaStream_t st)
 {
     a.perturb = (unsigned)p.perturb;
+    a.rows_flip = cluster_rows_flip(p.g, cc.C);
+    a.rec_col = p.d_igx;
+    a.rec_simple = p.rec_simple ? 1 : 0;
     const_cast<Plan &>(p).last_fwd_C = cc.C;
     const_cast<Plan &>(p).last_fwd_rows = cc.rmax;
     return dispatch_fwd_cluster(p, cc, a, st, nullptr);

@@ -313,6 +313,9 @@ int rdfwi_plan_create(const rdfwi_survey *s, rdfwi_plan *out)
     cudaError_t e = upload(&p->d_isx, s->isx, sizeof(int) * s->ns);
     if (e == cudaSuccess) e = upload(&p->d_rec_ptr, rec_ptr.data(), sizeof(int) * rec_ptr.size());
     if (e == cudaSuccess) e = upload(&p->d_rec_idx, rec_idx.data(), sizeof(int) * rec_idx.size());
+    if (e == cudaSuccess) e = upload(&p->d_igx, s->igx, sizeof(int) * s->nrec);
+    p->rec_simple = true;
+    for (int x = 0; x < nxp; ++x) p->rec_simple = p->rec_simple && rec_ptr[x + 1] - rec_ptr[x] <= 1;
     if (e == cudaSuccess) e = upload(&p->d_r2, r2.data(), sizeof(float) * r2.size());
     if (e == cudaSuccess) e = upload(&p->d_dkap, dkap.data(), sizeof(float) * dkap.size());
     if (e == cudaSuccess) e = upload(&p->d_wavelet, p->wavelet.data(), sizeof(float) * p->wavelet.size());
@@ -331,7 +334,7 @@ int rdfwi_plan_destroy(rdfwi_plan plan)
     Plan *p = reinterpret_cast<Plan *>(plan);
     DeviceGuard guard(p->device);
     clear_spans(p);
-    cudaFree(p->d_isx); cudaFree(p->d_rec_ptr); cudaFree(p->d_rec_idx); cudaFree(p->d_r2); cudaFree(p->d_dkap); cudaFree(p->d_wavelet);
+    cudaFree(p->d_isx); cudaFree(p->d_rec_ptr); cudaFree(p->d_rec_idx); cudaFree(p->d_igx); cudaFree(p->d_r2); cudaFree(p->d_dkap); cudaFree(p->d_wavelet);
     delete p;
     return RDFWI_OK;
 }

@@ -51,6 +51,8 @@ struct Plan {
     int *d_isx = nullptr;      // (ns)
     int *d_rec_ptr = nullptr;  // (nxp+1) CSR: receivers sitting in each padded column
     int *d_rec_idx = nullptr;  // (nrec)
+    int *d_igx = nullptr;      // (nrec) padded column of every receiver
+    bool rec_simple = false;   // no padded column holds more than one receiver
     float *d_r2 = nullptr;     // (nbc+1) (k*dx/a)^2, entry nbc = 0
     float *d_dkap = nullptr;   // (nbc+1) d(kappa*dt)/d(velmin) per profile entry, entry nbc = 0
     float *d_wavelet = nullptr;  // (nt) fp32 wavelet for the cluster-resident kernels
@@ -104,6 +106,9 @@ struct ClusterFwdArgs {
     float *Gb;              // adjoint mode: (B*ns) sum_t u_t[src] w_t / alpha_src
     int slabrows, ngroups, wav_smem;  // filled by launch_fwd_cluster from the ClusterConfig
     unsigned perturb;       // debug: seed of pseudo-random per-warp delays at the synchronisation points (0 = off)
+    int rows_flip;          // which CTAs take the nzp % C extra rows (filled by launch_fwd_cluster)
+    const int *rec_col;     // (nrec) padded column of every receiver
+    int rec_simple;         // no column holds more than one receiver: the receiver-major sampling / cotangent paths apply
 };
 
 struct ClusterConfig {
