@@ -680,9 +680,11 @@ static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, 
     if (device_attr(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p.device) != cudaSuccess) return false;
     for (int C = 1; C <= 16; ++C) {
         if (C > 8 && C != 16) continue;  // 1..8 are portable cluster sizes, 16 needs the non-portable opt-in
-        // 16-CTA clusters (31-row slabs, 8 co-resident clusters) lose to the tiled per-level engine on the grids that
-        // need them (interior 256^2: 1.25e11 vs 1.02e11 pairs/s at 16 shots, profiles/sweep_r1.md): only on request
-        if (C == 16 && !allow16 && p.cluster_size != 16 && p.engine != 2) continue;
+        // 16-CTA clusters (31-row slabs, 9 co-resident clusters): in round 1 they lost to the tiled per-level engine on the
+        // grids that need them (interior 256^2: 1.02e11 vs 1.25e11 pairs/s at 16 shots); with the resident adjoint and the
+        // coefficients in tensor memory they win by half (1.84e11 / 2.22e11 / 1.70e11 at 16 / 64 / 256 shots against
+        // 1.25e11 / 1.54e11 / 0.91e11, profiles/sweep_r2b.md), so they are part of the automatic choice now
+        (void)allow16;
         if (p.cluster_size > 0 && C != p.cluster_size) continue;
         if (g.nzp / C < 2) break;
         const int maxrows = (g.nzp + C - 1) / C;
