@@ -1,6 +1,7 @@
 // kernels_prologue.cu -- per-model coefficient data of the FD recurrence.
 //
-// Replaces, bit for bit in fp32, the prologue of FWIForward.FWM / forward in the reference:
+// Replaces, bit for bit in fp32 (against the reference run on the CPU: on CUDA PyTorch evaluates tensor / python_scalar as
+// a * (1/b), which differs from the __fdiv_rn below by up to 1 ulp), the prologue of FWIForward.FWM / forward in the reference:
 //   replicate padding ............. solvers/pde.py:91
 //   alpha = (v*dt/dx)**2 .......... solvers/pde.py:63
 //   velmin + sponge profile ....... solvers/pde.py:38-52 (get_Abc), kappa = abc*dt (:65)

@@ -90,6 +90,30 @@ def test_marmousi_many_shots_linspace_geometry(ns, nt, oracle):
     op.release_memory()
 
 
+@pytest.mark.parametrize("imaging", [0, 1])
+def test_sixteen_cta_clusters_at_sweep_size(oracle, imaging):
+    """BASELINE configs[4] sweep, interior 256^2 (padded 496 x 496: 984 KB per level, the largest grid that fits a cluster --
+    16 CTAs of 31 rows, the non-portable size, chosen automatically since round 2), three shots, 300 levels: bit-identical
+    seismograms, gradient against the pinned oracle, with the resident and with the split adjoint."""
+    from red_diffeq_b200 import FWIForward
+    n, nbc, nt = 256, 120, 300
+    ctx = dict(n_grid=n, nt=nt, dx=10.0, dt=0.001, nbc=nbc, f=15.0, sz=10, gz=10, ng=n, ns=3)
+    rng = np.random.default_rng(53)
+    z = np.linspace(0.0, 1.0, n, dtype=np.float32)[:, None]
+    v = (1500 + 2500 * z + 400 * rng.random((1, 1, n, n))).astype(np.float32)
+    sv = oracle.Survey(dict(ctx), n, n)
+    cot = rng.standard_normal((1, 3, nt, n)).astype(np.float32)
+    op = FWIForward(dict(ctx), "cuda:0", normalize=False)
+    op.set_option("imaging", imaging)
+    seis, grad = _run(op, v, cot)
+    plan = op._plan_for(n, n, torch.device("cuda:0"))
+    assert plan.get("cluster_size_last") == 16 and plan.get("adj_split") == (1 if imaging == 1 else 4)
+    seis_o, grad_o = oracle.gradient(sv, v, cot)
+    assert np.array_equal(seis, seis_o)
+    assert rel_l2(grad, grad_o) <= GRAD_TOL
+    op.release_memory()
+
+
 def test_tiled_engine_at_sweep_size(oracle):
     """BASELINE configs[4] sweep, interior 1024^2 (padded 1264 x 1264: the genuinely HBM-bound per-level engine), one shot,
     300 levels: bit-identical seismograms, gradient against the pinned oracle."""
