@@ -436,7 +436,7 @@ def measure_workload(env, workload, steps, warmup, opts=(), history_segment=None
     launches_f, launches_b = evs[-1][3], evs[-1][4]
 
     # ---- end-to-end timing from pinned host buffers (e2e) -------------------------------------------
-    for _ in range(min(warmup, 1)):
+    for _ in range(max(1, warmup)):   # (as many warm-up steps as the resident-input timing: the allocator pools of the e2e path)
         step_e2e()
     env.barrier()
     e_start = torch.cuda.Event(enable_timing=True)

@@ -173,7 +173,9 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             // (adjoint modes: kapx holds 1 - kappa_col and th.mz is negated, so the same FMA gives 1 - kappa directly)
             const float2 kp = f2fma(make_float2(th.mz[j], th.mz[j + 1]), make_float2(kapz, kapz), make_float2(kapx[j], kapx[j + 1]));
             float2 res;
-            if (EXACT) {  // forward wavefield: one rounding per reference op, products never packed (see above)
+            if (EXACT) {  // forward wavefield: one rounding per reference op
+                // (products stay scalar FMULs: ptxas contracts a packed product feeding a packed sum into FFMA2 even with .rn --
+                // and it also rewrites fma(a, b, -0) into that product first: measured, the checksum of the batch changed)
                 const float2 lap = f2add(make_float2(__fmul_rn(c2, s1.x), __fmul_rn(c2, s1.y)),
                                          make_float2(__fmul_rn(c3, s2.x), __fmul_rn(c3, s2.y)));
                 const float2 t1 = CTM ? make_float2(gk[j], gk[j + 1])
