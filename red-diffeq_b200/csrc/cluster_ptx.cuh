@@ -92,6 +92,7 @@ struct SweepThread {
     int x, la, lb;            // first column, local row range [la, lb)
     int lac;                  // la clamped into the slab for lanes that own nothing
     bool edgeL, edgeR;
+    bool swap;                // lanes 8-15 / 24-31: read the right neighbour pair first (conflict-free LDS.64, see fwd_sweep)
     int eL, eR;               // column offsets of the (x-2, x-1) / (x+4, x+5) pairs, periodic
     bool colsp[4];
     float mz[4];              // 0 in sponge columns (kappa follows the column profile), 1 elsewhere (row profile)

@@ -71,6 +71,14 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
     float *pb = smem + prv + (2 + l0) * pitch + th.x;              // row l0 of p_{t-2}; p_t goes there
     const float *eLp = smem + cur + (2 + l0) * pitch + th.eL;
     const float *eRp = smem + cur + (2 + l0) * pitch + th.eR;
+#ifndef RDFWI_PLAIN_PAIRS
+    // Bank-conflict-free neighbour pairs.  A lane reads 8 bytes 16 bytes apart from its neighbours': the left pairs of a
+    // warp only touch banks = 2, 3 (mod 4), the right pairs banks = 0, 1 (mod 4), so each LDS.64 is a 2-way conflict (4
+    // wavefronts instead of 2; 8 of a row's 27).  Let lanes 0-7 / 16-23 read their LEFT pair and lanes 8-15 / 24-31 their
+    // RIGHT pair in one instruction and the other way round in a second one: every 16-lane wavefront then covers all 32
+    // banks once.  Two selects per pair put the values back in place (the kernel is not issue-bound).
+    const float *pairA = th.swap ? eRp : eLp, *pairB = th.swap ? eLp : eRp;
+#endif
     const float *kz = smem + kap_off + l0;
     const float *push_dst = smem + prv + hp.dst + th.x;
     const int nvalid = th.lb - th.la;
@@ -132,8 +140,14 @@ __device__ __forceinline__ void fwd_sweep(float *__restrict__ smem, const int cu
             // production grids (even nxp, see the dispatcher): the two x-neighbour pairs are 8-byte aligned in the row that
             // sits in shared memory anyway -- two LDS.64 per row for every lane, instead of four shuffles plus four
             // predicated edge loads behind a divergent branch (ncu: BSSY/BSYNC stalls, ~18 of ~100 instructions per row)
+#ifdef RDFWI_PLAIN_PAIRS
             const float2 lp = *reinterpret_cast<const float2 *>(eLp + r * P);
             const float2 rp = *reinterpret_cast<const float2 *>(eRp + r * P);
+#else
+            const float2 qa = *reinterpret_cast<const float2 *>(pairA + r * P);
+            const float2 qb = *reinterpret_cast<const float2 *>(pairB + r * P);
+            const float2 lp = th.swap ? qb : qa, rp = th.swap ? qa : qb;
+#endif
             l2 = lp.x; l1 = lp.y; r0 = rp.x; r1 = rp.y;
         } else {
             // generic pitch: x-neighbours outside the float4 come from the adjacent lanes' centre vectors
@@ -306,6 +320,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     th.x = col * 4;
     th.la = grp * RMAX;
     th.lb = !active ? th.la : (th.la + RMAX < nrows ? th.la + RMAX : nrows);
+    th.swap = (lane_id & 8) != 0;
     th.edgeL = lane_id == 0 || col == 0;
     th.edgeR = lane_id == 31 || col == g.q4 - 1;
     th.eL = col == 0 ? g.nxp - 2 : th.x - 2;
