@@ -142,11 +142,15 @@ __device__ __forceinline__ void tile_body(const StepArgs &a, const Grid &g, floa
     const float *p0p = sP0 + lr0 * kTileW + 4 * lx;
     const float *alp_p = sAl + lr0 * kTileW + 4 * lx;
     float *outp = PO + (size_t)zt * pitch + x;
+    const bool swap = (lx & 8) != 0;
     float4 w0 = lds4(c1p), w1 = lds4(c1p + kRowW), w2 = lds4(c1p + 2 * kRowW), w3 = lds4(c1p + 3 * kRowW);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const float4 w4 = lds4(c1p + (r + 4) * kRowW);
-        const float2 lft = lds2(c1p + (r + 2) * kRowW - 2), rgt = lds2(c1p + (r + 2) * kRowW + 4);
+        // neighbour pairs without bank conflicts: lanes 0-7 / 16-23 read their left pair first, the others their right pair
+        // (see fwd_sweep in kernels_cluster.cu: a warp's left pairs only touch banks 2, 3 mod 4, its right pairs 0, 1 mod 4)
+        const float2 qa = lds2(c1p + (r + 2) * kRowW + (swap ? 4 : -2)), qb = lds2(c1p + (r + 2) * kRowW + (swap ? -2 : 4));
+        const float2 lft = swap ? qb : qa, rgt = swap ? qa : qb;
         const float4 old = lds4(p0p + r * kTileW);
         const float4 al = lds4(alp_p + r * kTileW);
         const float e[8] = {lft.x, lft.y, w2.x, w2.y, w2.z, w2.w, rgt.x, rgt.y};
