@@ -4,15 +4,21 @@
 // Replaces the same reference code as kernels_step.cu (the hot loop solvers/pde.py:78-85 and, for the
 // adjoint, the autograd replay behind core/inversion.py:86) with identical arithmetic, but removes the
 // per-level HBM round trip of the wavefields: a padded OpenFWI shot is 2 x 387 KB (p_{t-1}, p_{t-2}),
-// which fits the shared memory of a 4-CTA cluster.  Per level each CTA
+// which fits the shared memory of a 4-CTA cluster.  One persistent launch runs all levels of all shots
+// (clusters take shots round-robin); per level each CTA
 //   1. updates its slab of rows in place (p_t overwrites p_{t-2}: a cell needs p_{t-2} only at itself),
-//      z-marching in registers, x-neighbours by warp shuffle;
+//      z-marching in registers, x-neighbour pairs from the resident row (conflict-free LDS.64, fwd_sweep);
 //   2. pushes its two first / last rows into the neighbours' halo rows through distributed shared memory
-//      (st.shared::cluster), periodic in z like torch.roll;
-//   3. one barrier.cluster (release/acquire) closes the level;
-//   4. an elected thread streams the slab to the wavefield history with a 1-D bulk copy
-//      (cp.async.bulk shared -> global), overlapped with the next level.
-// HBM traffic: forward = the history write only (4 B / cell-update instead of 12).
+//      (st.async ... mbarrier::complete_tx), periodic in z like torch.roll -- no cluster barrier in the loop;
+//   3. forward (MODE 0): an elected thread streams the slab to the wavefield history with a 1-D bulk copy
+//      (cp.async.bulk shared -> global), overlapped with the next level; the time-invariant coefficient
+//      rows (alpha, t1) come from TENSOR MEMORY, used as a per-thread scratchpad (cluster_ptx.cuh);
+//      adjoint (MODE 2, the default): the forward history streams IN (cp.async into thread-private
+//      slots) and the zero-lag imaging sums are formed in the same sweep, their accumulators in tensor
+//      memory -- the adjoint field never leaves the chip.  (MODE 1 + kernels_imaging.cu: the split adjoint
+//      of round 1, kept as an option and as the cross-check.)
+// HBM traffic: the history, written once by the forward and read once by the adjoint: 8 B per
+// forward+adjoint cell-update pair instead of the 28 B a streaming implementation moves.
 #include <mutex>
 
 #include "cluster_ptx.cuh"
@@ -21,8 +27,8 @@ namespace rdfwi {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ forward
-// Hot loop notes (from the ncu captures under profiles/): the kernel is issue-bound and, in its first
-// versions, lost half of its cycles at a per-level barrier.cluster (MEMBAR.ALL.GPU + skew).  Hence:
+// Hot loop notes (from the ncu captures under profiles/): in its first versions the kernel lost half of its
+// cycles at a per-level barrier.cluster (MEMBAR.ALL.GPU + skew) and was issue-bound.  Hence:
 //   * PITCH is a template parameter for the production grids (0 = runtime pitch), so every row offset is
 //     an immediate of the LDS/STS instruction;
 //   * rows a thread does not own are still computed (from in-bounds garbage), only their store is predicated;
