@@ -281,8 +281,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
 #endif
     constexpr int ATM = !IMG ? 0 : ((128 - 8 * RMAX) / 4 < RMAX ? (128 - 8 * RMAX) / 4 : RMAX);
     static_assert(!IMG || 8 * RMAX + 4 * ATM <= 128, "tensor-memory columns per thread");
-    extern __shared__ __align__(128) float smem[];
-    __shared__ uint32_t s_tmem;
+    extern __shared__ __align__(128) float smem[];  // (no static shared memory: the launch sizes the block to the last byte)
 
     const int C = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
     const int cid = blockIdx.x / C, ncl = gridDim.x / C;
@@ -306,7 +305,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) k_fwd_cluster(ClusterFwdAr
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ((kap_off + a.slabrows + 3) & ~3));
     // small read-only tables staged once per kernel so the epilogue never waits on global memory:
     // receiver CSR (columns -> receiver slots) and, when it fits, the wavelet
-    float *s_prow = reinterpret_cast<float *>(bars + 4);  // [2][pitch] receiver row of the forward level (MODE 2), 16-byte aligned
+    uint32_t &s_tmem = *reinterpret_cast<uint32_t *>(bars + 4);  // base address of the tensor-memory allocation
+    float *s_prow = reinterpret_cast<float *>(bars + 4) + 4;  // [2][pitch] receiver row of the forward level (MODE 2), 16-byte aligned
     float *s_ginj = s_prow + 2 * pitch;                   // [pitch] sum_t p_t[rec] g_t per column (MODE 2)
     int *s_rec_ptr = reinterpret_cast<int *>(s_ginj + pitch);
     int *s_rec_idx = s_rec_ptr + g.nxp + 1;

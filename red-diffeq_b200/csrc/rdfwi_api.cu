@@ -24,6 +24,7 @@ namespace {
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess) {                                                                   \
+            cudaGetLastError(); /* a failed launch must not be reported again by the next call */  \
             set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                         \
             return RDFWI_ECUDA;                                                                    \
         }                                                                                          \

@@ -114,6 +114,49 @@ def test_sixteen_cta_clusters_at_sweep_size(oracle, imaging):
     op.release_memory()
 
 
+def test_grid_that_fits_a_cluster_only_without_the_staging_slots(oracle):
+    """Interior 360^2 (padded 600 x 600): the slabs of a 16-CTA cluster leave no room for the resident adjoint's staging slots,
+    so the backward pass falls back to the split adjoint (adjoint-field history + streaming imaging kernel) on the cluster
+    engine by itself; the forward pass is the cluster engine's either way."""
+    from red_diffeq_b200 import FWIForward
+    n, nbc, nt = 360, 120, 200
+    ctx = dict(n_grid=n, nt=nt, dx=10.0, dt=0.001, nbc=nbc, f=15.0, sz=10, gz=10, ng=n, ns=2)
+    rng = np.random.default_rng(54)
+    v = (1500 + 3000 * rng.random((1, 1, n, n))).astype(np.float32)
+    sv = oracle.Survey(dict(ctx), n, n)
+    cot = rng.standard_normal((1, 2, nt, n)).astype(np.float32)
+    op = FWIForward(dict(ctx), "cuda:0", normalize=False)
+    seis, grad = _run(op, v, cot)
+    plan = op._plan_for(n, n, torch.device("cuda:0"))
+    assert plan.get("cluster_size_last") == 16 and plan.get("adj_split") in (1, 4)
+    seis_o, grad_o = oracle.gradient(sv, v, cot)
+    assert np.array_equal(seis, seis_o)
+    assert rel_l2(grad, grad_o) <= GRAD_TOL
+    op.release_memory()
+
+
+@pytest.mark.parametrize("n", [290, 300, 316, 330, 331, 344, 352, 360, 372, 380])
+def test_grids_at_the_edge_of_what_fits_a_cluster(n):
+    """Interior sizes around the largest grid whose slabs fit a 16-CTA cluster: every launch is sized to the last byte of
+    shared memory (n = 330 once failed with `invalid argument`: 72 bytes of room, and a 4-byte static variable the sizing
+    did not know about), the resident adjoint gives way to the split adjoint when its staging slots do not fit, and beyond
+    that the per-level engine takes over.  Whatever runs, the resident / default path must agree with the split adjoint."""
+    from red_diffeq_b200 import FWIForward
+    nt = 160
+    ctx = dict(n_grid=n, nt=nt, dx=10.0, dt=0.001, nbc=120, f=30.0, sz=10, gz=10, ng=n, ns=2)
+    rng = np.random.default_rng(n)
+    v = (1500 + 3000 * rng.random((1, 1, n, n))).astype(np.float32)
+    cot = rng.standard_normal((1, 2, nt, n)).astype(np.float32)
+    a = FWIForward(dict(ctx), "cuda:0", normalize=False)
+    seis_a, grad_a = _run(a, v, cot)
+    b = FWIForward(dict(ctx), "cuda:0", normalize=False)
+    b.set_option("imaging", 1)
+    seis_b, grad_b = _run(b, v, cot)
+    assert np.isfinite(grad_a).all() and np.array_equal(seis_a, seis_b)
+    assert rel_l2(grad_a, grad_b) <= GRAD_TOL
+    a.release_memory(); b.release_memory()
+
+
 def test_tiled_engine_at_sweep_size(oracle):
     """BASELINE configs[4] sweep, interior 1024^2 (padded 1264 x 1264: the genuinely HBM-bound per-level engine), one shot,
     300 levels: bit-identical seismograms, gradient against the pinned oracle."""
