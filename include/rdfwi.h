@@ -76,7 +76,7 @@ int rdfwi_plan_destroy(rdfwi_plan plan);
  *   "u_chunk_shots"  shots per chunk of the split adjoint (0 = auto: whole waves of co-resident clusters)
  *   "scratch_mb"     cap on one scratch history of the split adjoint, MB (0 = 40000; 55000 for the recompute tier)
  *   "cluster_size"   CTAs per cluster of the cluster-resident time loop (0 = smallest of 1..8 that fits)
- *   "cluster_rows"   rows marched per thread by the cluster-resident time loop: 13, 7 or 4 (0 = auto: 13, or 7 / 4 on a
+ *   "cluster_rows"   rows marched per thread by the cluster-resident time loop: 13, 7, 5 or 4 (0 = auto: 13, or fewer on a
  *                    wider cluster when a launch has so few shots that each still gets its own co-resident cluster)
  *   "rows_per_thread" (1, 2, 4, 8; tile rows = 8x) / "adj_rows_per_thread"  z-rows marched per thread, per-level kernels
  *   "chunk_models"   models advanced together by the per-level forward (0 = auto)

@@ -739,11 +739,20 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots, bool img)
     // the same time alone as among 33 co-resident ones), so spread a shot over more CTAs with fewer rows per thread --
     // as long as every shot of the launch still gets its own co-resident cluster.
     if (2 * nshots * cfg->C > 148) return true;
-    static const int kWideRows[2] = {4, 7};
-    for (int i = 0; i < 2; ++i) {
+    // Among the wide configurations that give every shot its own co-resident cluster, the cheapest level: a level is the
+    // sweep of the busiest scheduler -- (row-owning warps per scheduler) x (rows marched + ~1.3 rows of start-up loads) --
+    // and two warps per scheduler hide too little latency (measured, one OpenFWI model on 16-CTA clusters: 4 rows 3.73 ms,
+    // 5 rows 3.39 ms, 6 rows 3.72 ms, 7 rows 3.66 ms per gradient; one Marmousi-shaped model: 7 rows 4.21, 6 rows 4.50).
+    static const int kWideRows[3] = {4, 5, 7};
+    float best = 1e30f;
+    const int base_C = cfg->C;
+    for (int i = 0; i < 3; ++i) {
         ClusterConfig wide;
-        if (!cluster_config_rows(p, kWideRows[i], true, &wide, img) || wide.C <= cfg->C) continue;
-        if (fwd_cluster_wave(p, wide) >= nshots) { *cfg = wide; return true; }
+        if (!cluster_config_rows(p, kWideRows[i], true, &wide, img) || wide.C <= base_C) continue;
+        if (fwd_cluster_wave(p, wide) < nshots) continue;
+        const int warps = (wide.ngroups * p.g.q4 + 31) / 32, per_sched = (warps + 3) / 4;
+        const float cost = per_sched * (kWideRows[i] + 1.3f) + (per_sched < 3 ? 6.0f : 0.0f);
+        if (cost < best) { best = cost; *cfg = wide; }
     }
     return true;
 }
@@ -842,6 +851,7 @@ static cudaError_t dispatch_fwd_cluster(const Plan &p, const ClusterConfig &cc, 
         case 7: return dispatch_fwd_cluster_r<7>(p, cc, a, st, wave_only);
 #endif
         case 4: return dispatch_fwd_cluster_r<4>(p, cc, a, st, wave_only);
+        case 5: return dispatch_fwd_cluster_r<5>(p, cc, a, st, wave_only);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -359,7 +359,7 @@ int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value)
     else if (k == "img_prefetch") { if (value < 0 || value > 64) goto bad; p->img_prefetch = (int)value; }
     else if (k == "trace_ptr") { p->trace_ptr = reinterpret_cast<long long *>(value); }
     else if (k == "cluster_size") { if (value < 0 || (value > 8 && value != 16)) goto bad; p->cluster_size = (int)value; }
-    else if (k == "cluster_rows") { if (value != 0 && value != 4 && value != 7 && value != kClusterRowsMax) goto bad; p->cluster_rows = (int)value; }
+    else if (k == "cluster_rows") { if (value != 0 && value != 4 && value != 5 && value != 7 && value != kClusterRowsMax) goto bad; p->cluster_rows = (int)value; }
     else { set_error("unknown option " + k); return RDFWI_EINVAL; }
     return RDFWI_OK;
 bad:

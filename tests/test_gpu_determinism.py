@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name,opts,reps", [
-    ("openfwi", {}, 150),                                   # 5 shots -> 16-CTA clusters, 4 rows per thread
+    ("openfwi", {}, 150),                                   # 5 shots -> 16-CTA clusters, 5 rows per thread
+    ("openfwi", {"cluster_rows": 4}, 100),                  # (the configuration the wrong wait showed up in)
     ("openfwi", {"cluster_rows": 7}, 60),
     ("openfwi", {"cluster_rows": 13}, 60),
     ("openfwi", {"imaging": 1}, 40),                        # split adjoint

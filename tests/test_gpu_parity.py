@@ -138,9 +138,11 @@ def test_recomputed_history_matches_full_history(name, chunk, imaging):
 
 @pytest.mark.parametrize("name,rows,csize", [("tiny_default", 4, 0), ("tiny_default", 4, 3), ("tiny_custom", 7, 2),
                                              ("tiny_half_receivers", 4, 5), ("tiny_half_receivers", 7, 0),
-                                             ("openfwi", 7, 0), ("openfwi", 4, 0), ("marmousi", 7, 0), ("marmousi", 13, 8)])
+                                             ("openfwi", 7, 0), ("openfwi", 4, 0), ("marmousi", 7, 0), ("marmousi", 13, 8),
+                                             ("tiny_default", 5, 2), ("tiny_custom", 5, 0), ("openfwi", 5, 0), ("openfwi", 5, 16),
+                                             ("marmousi", 5, 16)])
 def test_wide_cluster_configurations(name, rows, csize):
-    """Few-shot configurations of the cluster-resident time loop (a shot spread over more CTAs, 7 or 4 rows marched per
+    """Few-shot configurations of the cluster-resident time loop (a shot spread over more CTAs, 7, 5 or 4 rows marched per
     thread instead of 13): same arithmetic per cell => seismograms bit-identical to the reference fixtures and gradients
     bit-identical to the throughput configuration (13 rows, smallest cluster)."""
     g = Golden(name)

@@ -47,6 +47,7 @@ CASES = [  # fixture, rows per thread, cluster size (0 = smallest that fits), se
     ("tiny_half_receivers", 13, 2, 20, 0),
     ("openfwi", 13, 0, 6, 0), ("openfwi", 7, 0, 6, 0), ("openfwi", 4, 0, 6, 0), ("openfwi", 13, 6, 4, 0),
     ("marmousi", 13, 0, 6, 0), ("marmousi", 7, 0, 6, 0), ("marmousi", 13, 8, 4, 0),
+    ("tiny_default", 5, 2, 20, 0), ("openfwi", 5, 0, 6, 0), ("marmousi", 5, 16, 4, 0),
     ("tiny_default", 13, 0, 10, 1), ("tiny_custom", 7, 2, 10, 1), ("openfwi", 13, 0, 4, 1), ("marmousi", 7, 0, 4, 1),
 ]
 
