@@ -740,9 +740,9 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots, bool img)
     // as long as every shot of the launch still gets its own co-resident cluster.
     if (2 * nshots * cfg->C > 148) return true;
     // Among the wide configurations that give every shot its own co-resident cluster, the cheapest level: a level is the
-    // sweep of the busiest scheduler -- (row-owning warps per scheduler) x (rows marched + ~1.3 rows of start-up loads) --
+    // sweep of the busiest scheduler -- (row-owning warps per scheduler) x (rows marched + ~1 row of start-up loads) --
     // and two warps per scheduler hide too little latency (measured, one OpenFWI model on 16-CTA clusters: 4 rows 3.73 ms,
-    // 5 rows 3.39 ms, 6 rows 3.72 ms, 7 rows 3.66 ms per gradient; one Marmousi-shaped model: 7 rows 4.21, 6 rows 4.50).
+    // 5 rows 3.39 ms, 6 rows 3.72 ms, 7 rows 3.66 ms per gradient; one Marmousi-shaped model: 5 rows 4.16, 7 rows 4.21, 6 rows 4.50).
     static const int kWideRows[3] = {4, 5, 7};
     float best = 1e30f;
     const int base_C = cfg->C;
@@ -751,7 +751,7 @@ bool cluster_config(const Plan &p, ClusterConfig *cfg, int nshots, bool img)
         if (!cluster_config_rows(p, kWideRows[i], true, &wide, img) || wide.C <= base_C) continue;
         if (fwd_cluster_wave(p, wide) < nshots) continue;
         const int warps = (wide.ngroups * p.g.q4 + 31) / 32, per_sched = (warps + 3) / 4;
-        const float cost = per_sched * (kWideRows[i] + 1.3f) + (per_sched < 3 ? 6.0f : 0.0f);
+        const float cost = per_sched * (kWideRows[i] + 1.0f) + (per_sched < 3 ? 6.0f : 0.0f);
         if (cost < best) { best = cost; *cfg = wide; }
     }
     return true;

@@ -174,7 +174,7 @@ def test_few_shots_pick_a_wide_cluster():
     s, _ = _run(op, g.v)
     plan = op._plan_for(70, 70, torch.device("cuda:0"))
     assert np.array_equal(s[:, :, ::g.seis_stride, :], g.seis_f32)
-    assert plan.get("cluster_rows_last") in (4, 7) and plan.get("cluster_size_last") > plan.get("cluster_size_used")
+    assert plan.get("cluster_rows_last") in (4, 5, 7) and plan.get("cluster_size_last") > plan.get("cluster_size_used")
     many = np.repeat(g.v, 16, axis=0)
     s16, _ = _run(op, many)
     assert plan.get("cluster_rows_last") == 13 and plan.get("cluster_size_last") == plan.get("cluster_size_used")
