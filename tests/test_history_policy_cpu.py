@@ -15,7 +15,7 @@ class FakePlan:
 
     def __init__(self, nt=1000, ns=5, level_floats=96720, clustered=True, wave=33):
         self.nt, self.ns, self._level, self.clustered, self.wave = nt, ns, level_floats, clustered, wave
-        self.opts = {"history_segment": 0, "adj_mode": 0, "u_chunk_shots": 0, "scratch_mb": 0}
+        self.opts = {"history_segment": 0, "adj_mode": 0, "u_chunk_shots": 0, "scratch_mb": 0, "imaging": 0}
         self.log = []
         self.size_queries = 0
 
@@ -50,6 +50,8 @@ class FakePlan:
         if seg and seg < self.nt:                           # checkpoints in time: one recomputed segment
             return small + 4.0 * self._level * shots * (seg - 1)
         if o["adj_mode"] == 1 and not seg:                  # fused adjoint: no scratch history
+            return small
+        if self.clustered and o["imaging"] != 1 and not seg:  # resident imaging (default): the adjoint field stays on chip
             return small
         cap = o["scratch_mb"] * 1e6 if o["scratch_mb"] else (55 * GB if seg else 40 * GB)
         chunk = o["u_chunk_shots"] or max(1, int(cap // per_shot))
@@ -90,6 +92,19 @@ def test_long_record_prefers_recomputing_over_the_fused_adjoint(monkeypatch):
     plan = FakePlan(nt=16000, level_floats=310 * 432, wave=22)             # 8.6 GB per shot: < a wave of shots per 40 GB
     seg, _ = op._choose_segment(plan, 8, torch.device("cuda:0"))
     assert seg == plan.nt and plan.opts["adj_mode"] == 0
+
+
+def test_long_record_that_fits_is_kept_unless_the_split_adjoint_is_asked_for(monkeypatch):
+    """bench workload overthrust_long: 8 Marmousi-shaped models x nt = 4000 = 85.7 GB of history.  With the imaging sums formed
+    in the adjoint sweep (default) nothing else is needed and every level is kept; the split adjoint's scratch history would
+    hold less than a wave of shots there, so with imaging = 1 the policy recomputes the forward field instead."""
+    op = _op(monkeypatch, 178)
+    plan = FakePlan(nt=4000, level_floats=310 * 432, wave=22)
+    assert op._choose_segment(plan, 8, torch.device("cuda:0")) == (0, {})
+    op.set_option("imaging", 1)
+    plan.opts["imaging"] = 1
+    seg, _ = op._choose_segment(plan, 8, torch.device("cuda:0"))
+    assert seg == plan.nt
 
 
 def test_little_memory_falls_back_to_checkpoints_in_time(monkeypatch):
