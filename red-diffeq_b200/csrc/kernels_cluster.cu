@@ -705,8 +705,8 @@ static bool cluster_config_rows(const Plan &p, const int R, const bool allow16, 
         if (C > 8 && C != 16) continue;  // 1..8 are portable cluster sizes, 16 needs the non-portable opt-in
         // 16-CTA clusters (31-row slabs, 9 co-resident clusters): in round 1 they lost to the tiled per-level engine on the
         // grids that need them (interior 256^2: 1.02e11 vs 1.25e11 pairs/s at 16 shots); with the resident adjoint and the
-        // coefficients in tensor memory they win by half (1.84e11 / 2.22e11 / 1.70e11 at 16 / 64 / 256 shots against
-        // 1.25e11 / 1.54e11 / 0.91e11, profiles/sweep_r2b.md), so they are part of the automatic choice now
+        // coefficients in tensor memory they win by half (2.00e11 / 2.42e11 / 1.86e11 at 16 / 64 / 256 shots against
+        // 1.25e11 / 1.54e11 / 0.91e11, profiles/sweep_r2b_n1.md), so they are part of the automatic choice now
         (void)allow16;
         if (p.cluster_size > 0 && C != p.cluster_size) continue;
         if (g.nzp / C < 2) break;
@@ -827,6 +827,15 @@ static cudaError_t dispatch_fwd_cluster_rp(const Plan &p, const ClusterConfig &c
                              : launch_fwd_cluster_t<R, PITCH, 0, false>(p, cc, a, st, wave_only);
 }
 
+// throughput configuration only (13 rows, no perturbation): the sweep-table grids interior 128^2 and 256^2 (BASELINE config 5)
+template <int PITCH>
+static cudaError_t dispatch_fwd_cluster_sweep_grid(const Plan &p, const ClusterConfig &cc, const ClusterFwdArgs &a, cudaStream_t st, int *wave_only)
+{
+    return a.adj_mode == 2   ? launch_fwd_cluster_t<kClusterRowsMax, PITCH, 2, false>(p, cc, a, st, wave_only)
+           : a.adj_mode == 1 ? launch_fwd_cluster_t<kClusterRowsMax, PITCH, 1, false>(p, cc, a, st, wave_only)
+                             : launch_fwd_cluster_t<kClusterRowsMax, PITCH, 0, false>(p, cc, a, st, wave_only);
+}
+
 template <int R>
 static cudaError_t dispatch_fwd_cluster_r(const Plan &p, const ClusterConfig &cc, const ClusterFwdArgs &a, cudaStream_t st, int *wave_only)
 {
@@ -836,6 +845,10 @@ static cudaError_t dispatch_fwd_cluster_r(const Plan &p, const ClusterConfig &cc
         case 312: return dispatch_fwd_cluster_rp<R, 312>(p, cc, a, st, wave_only);
 #ifndef RDFWI_DEV_FAST
         case 432: return dispatch_fwd_cluster_rp<R, 432>(p, cc, a, st, wave_only);
+        case 368: if (R == kClusterRowsMax && a.perturb == 0) return dispatch_fwd_cluster_sweep_grid<368>(p, cc, a, st, wave_only);
+                  return dispatch_fwd_cluster_rp<R, 0>(p, cc, a, st, wave_only);
+        case 496: if (R == kClusterRowsMax && a.perturb == 0) return dispatch_fwd_cluster_sweep_grid<496>(p, cc, a, st, wave_only);
+                  return dispatch_fwd_cluster_rp<R, 0>(p, cc, a, st, wave_only);
         default: return dispatch_fwd_cluster_rp<R, 0>(p, cc, a, st, wave_only);
 #else
         default: return cudaErrorInvalidValue;
