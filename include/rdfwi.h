@@ -75,7 +75,7 @@ int rdfwi_plan_destroy(rdfwi_plan plan);
  *                    argument of forward/backward must equal it)
  *   "u_chunk_shots"  shots per chunk of the split adjoint (0 = auto: whole waves of co-resident clusters)
  *   "scratch_mb"     cap on one scratch history of the split adjoint, MB (0 = 40000; 55000 for the recompute tier)
- *   "cluster_size"   CTAs per cluster of the cluster-resident time loop (0 = smallest of 1..8 that fits)
+ *   "cluster_size"   CTAs per cluster of the cluster-resident time loop (0 = smallest of 1..8 or 16 that fits)
  *   "cluster_rows"   rows marched per thread by the cluster-resident time loop: 13, 7, 5 or 4 (0 = auto: 13, or fewer on a
  *                    wider cluster when a launch has so few shots that each still gets its own co-resident cluster)
  *   "rows_per_thread" (1, 2, 4, 8; tile rows = 8x) / "adj_rows_per_thread"  z-rows marched per thread, per-level kernels
@@ -91,7 +91,8 @@ int rdfwi_plan_destroy(rdfwi_plan plan);
  * rdfwi_plan_get additionally answers "pitch", "nzp", "nxp", "nt_out", "cluster_size_used", "cluster_size_last", "cluster_rows_last" (what the
  * last cluster-resident launch ran),
  * "cluster_wave" (co-resident clusters of the forward configuration), "adj_split" (what the last backward ran: 0 per-level fused,
- * 1 cluster split, 2 cluster split on a recomputed forward history, 3 per-level split), "u_chunk_used". */
+ * 1 cluster split, 2 cluster split on a recomputed forward history, 3 per-level split, 4 cluster resident -- the imaging sums
+ * formed inside the adjoint sweep --, 5 cluster resident on a recomputed forward history), "u_chunk_used". */
 int rdfwi_plan_set(rdfwi_plan plan, const char *key, int64_t value);
 int rdfwi_plan_get(rdfwi_plan plan, const char *key, int64_t *value_out);
 
